@@ -1,0 +1,233 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU fp32 restatement of the reference FRNet.
+
+Functional (no nn.Module): parameters travel as an OrderedDict keyed exactly
+like the reference ``FRNet.state_dict()``, so a reference
+checkpoint is directly usable.  Dense contractions use torch's CPU conv
+(``F.conv2d`` -- the same third-party arithmetic the reference calls through
+``nn.Conv2d``); every sampling / index op uses the closed forms of
+``ops_oracle`` (numpy) so the oracle does not depend on grid_sample /
+interpolate / ConvTranspose2d semantics.
+
+Reference: codes/models/networks/tecogan_nets.py (FNet :16-82, ResidualBlock
+:85-100, SRNet :103-147, FRNet :150-281), codes/utils/net_utils.py:36-156,
+codes/utils/data_utils.py:80-87.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops_oracle as K
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def _conv3x3(x, p, name, act=None):
+    """nn.Conv2d(cin, cout, 3, 1, 1, bias=True) [+ activation]."""
+    y = F.conv2d(x, p[name + '.weight'], p[name + '.bias'], stride=1, padding=1)
+    if act == 'lrelu':      # nn.LeakyReLU(0.2)  -- FNet only (tecogan_nets.py:23-65)
+        y = torch.where(y >= 0, y, y * 0.2)
+    elif act == 'relu':     # nn.ReLU            -- SRNet (tecogan_nets.py:94,113,121,126)
+        y = torch.clamp_min(y, 0)
+    return y
+
+
+# ----------------------------------------------------------------------------
+# upsample_func  (codes/utils/net_utils.py:85-97)
+# ----------------------------------------------------------------------------
+def upsample_func(x, scale, degradation):
+    if degradation == 'BD':
+        return _t(K.bicubic_upsample(x.numpy(), scale))
+    if degradation == 'BI':
+        return _t(K.bilinear_upsample(x.numpy(), scale))
+    raise ValueError(f'Unrecognized degradation type: {degradation}')
+
+
+# ----------------------------------------------------------------------------
+# FNet.forward  (tecogan_nets.py:67-82)
+# ----------------------------------------------------------------------------
+def fnet_forward(p, x1, x2, prefix='fnet.'):
+    """flow from x1 (curr) to x2 (prev); output (8*floor(h/8), 8*floor(w/8))."""
+    out = torch.cat([x1, x2], dim=1)
+    for enc in ('encoder1', 'encoder2', 'encoder3'):
+        out = _conv3x3(out, p, f'{prefix}{enc}.0', 'lrelu')
+        out = _conv3x3(out, p, f'{prefix}{enc}.2', 'lrelu')
+        out = _t(K.maxpool2x2(out.numpy()))
+    for dec in ('decoder1', 'decoder2', 'decoder3'):
+        out = _conv3x3(out, p, f'{prefix}{dec}.0', 'lrelu')
+        out = _conv3x3(out, p, f'{prefix}{dec}.2', 'lrelu')
+        out = _t(K.bilinear_upsample(out.numpy(), 2))
+    out = _conv3x3(out, p, f'{prefix}flow.0', 'lrelu')
+    out = _conv3x3(out, p, f'{prefix}flow.2', None)
+    return torch.tanh(out) * 24  # 24 is the max velocity (tecogan_nets.py:80)
+
+
+# ----------------------------------------------------------------------------
+# SRNet.forward  (tecogan_nets.py:136-147)
+# ----------------------------------------------------------------------------
+def srnet_forward(p, lr_curr, hr_prev_tran, scale, degradation, nb=None,
+                  prefix='srnet.', taps=None):
+    out = _conv3x3(torch.cat([lr_curr, hr_prev_tran], dim=1), p, f'{prefix}conv_in.0', 'relu')
+    if taps is not None:
+        taps['conv_in'] = out
+    if nb is None:
+        nb = len({k.split('.')[2] for k in p if k.startswith(f'{prefix}resblocks.')})
+    for i in range(nb):
+        y = _conv3x3(out, p, f'{prefix}resblocks.{i}.conv.0', 'relu')
+        y = _conv3x3(y, p, f'{prefix}resblocks.{i}.conv.2', None)
+        out = y + out
+    if taps is not None:
+        taps['resblocks'] = out
+    n_up = 2 if scale == 4 else 1
+    for u in range(n_up):
+        key = f'{prefix}conv_up.{2 * u}'
+        out = _t(K.conv_transpose3x3s2_parity(out.numpy(), p[key + '.weight'].numpy(),
+                                              p[key + '.bias'].numpy()))
+        out = torch.clamp_min(out, 0)
+    if taps is not None:
+        taps['conv_up'] = out
+    out = _conv3x3(out, p, f'{prefix}conv_out', None)
+    out = out + upsample_func(lr_curr, scale, degradation)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# FRNet.step  (tecogan_nets.py:227-252)
+# ----------------------------------------------------------------------------
+def frnet_step(p, lr_curr, lr_prev, hr_prev, scale, degradation, taps=None,
+               exact_reference_grid=True):
+    lr_flow = fnet_forward(p, lr_curr, lr_prev)
+    pad_h = lr_curr.size(2) - lr_curr.size(2) // 8 * 8
+    pad_w = lr_curr.size(3) - lr_curr.size(3) // 8 * 8
+    lr_flow_pad = _t(K.reflect_pad_flow(lr_flow.numpy(), pad_h, pad_w))
+    hr_flow = scale * upsample_func(lr_flow_pad, scale, degradation)
+    cat = _t(K.warp_s2d_concat(hr_prev.numpy(), hr_flow.numpy(), lr_curr.numpy(), scale,
+                               exact_reference_grid))
+    c = lr_curr.size(1)
+    if taps is not None:
+        taps['lr_flow'] = lr_flow
+        taps['hr_flow'] = hr_flow
+        taps['srnet_in'] = cat
+    return srnet_forward(p, cat[:, :c], cat[:, c:], scale, degradation, taps=taps)
+
+
+# ----------------------------------------------------------------------------
+# FRNet.infer_sequence  (tecogan_nets.py:254-281)
+# ----------------------------------------------------------------------------
+def frnet_infer_sequence(p, lr_data, scale, degradation, return_float=False):
+    """lr_data [T,C,h,w] fp32 -> uint8 [T,H,W,C]; state starts at zeros."""
+    tot, c, h, w = lr_data.shape
+    s = scale
+    lr_prev = torch.zeros(1, c, h, w)
+    hr_prev = torch.zeros(1, c, s * h, s * w)
+    seq, fseq = [], []
+    for i in range(tot):
+        lr_curr = lr_data[i:i + 1]
+        hr_curr = frnet_step(p, lr_curr, lr_prev, hr_prev, scale, degradation)
+        lr_prev, hr_prev = lr_curr, hr_curr
+        fseq.append(hr_curr[0].numpy())
+        seq.append(K.float32_to_uint8(hr_curr[0].numpy()))
+    out = np.stack(seq).transpose(0, 2, 3, 1)  # thwc
+    if return_float:
+        return out, np.stack(fseq)
+    return out
+
+
+# ----------------------------------------------------------------------------
+# FRNet.forward_sequence  (tecogan_nets.py:174-225)  -- training forward
+# ----------------------------------------------------------------------------
+def frnet_forward_sequence(p, lr_data, scale, degradation):
+    n, t, c, lr_h, lr_w = lr_data.shape
+    hr_h, hr_w = lr_h * scale, lr_w * scale
+    lr_prev = lr_data[:, :-1].reshape(n * (t - 1), c, lr_h, lr_w)
+    lr_curr = lr_data[:, 1:].reshape(n * (t - 1), c, lr_h, lr_w)
+    lr_flow = fnet_forward(p, lr_curr, lr_prev)
+    hr_flow = scale * upsample_func(lr_flow, scale, degradation)
+    hr_flow = hr_flow.view(n, t - 1, 2, hr_h, hr_w)
+    hr_data = []
+    hr_prev = srnet_forward(p, lr_data[:, 0], torch.zeros(n, scale * scale * c, lr_h, lr_w),
+                            scale, degradation)
+    hr_data.append(hr_prev)
+    for i in range(1, t):
+        cat = _t(K.warp_s2d_concat(hr_prev.numpy(), hr_flow[:, i - 1].numpy(),
+                                   lr_data[:, i].numpy(), scale))
+        hr_curr = srnet_forward(p, cat[:, :c], cat[:, c:], scale, degradation)
+        hr_data.append(hr_curr)
+        hr_prev = hr_curr
+    return {
+        'hr_data': torch.stack(hr_data, dim=1),
+        'hr_flow': hr_flow,
+        'lr_prev': lr_prev,
+        'lr_curr': lr_curr,
+        'lr_flow': lr_flow,
+    }
+
+
+# ----------------------------------------------------------------------------
+# deterministic weights with the reference's state_dict layout
+# ----------------------------------------------------------------------------
+def frnet_param_shapes(in_nc=3, out_nc=3, nf=64, nb=10, scale=4, degradation='BD'):
+    shapes = OrderedDict()
+
+    def conv(name, cin, cout):
+        shapes[name + '.weight'] = (cout, cin, 3, 3)
+        shapes[name + '.bias'] = (cout,)
+
+    if degradation == 'BD':
+        shapes['upsample_func.kernels'] = (scale, 4)
+    chans = [('encoder1', 2 * in_nc, 32, 32), ('encoder2', 32, 64, 64), ('encoder3', 64, 128, 128),
+             ('decoder1', 128, 256, 256), ('decoder2', 256, 128, 128), ('decoder3', 128, 64, 64)]
+    for nm, a, b, c2 in chans:
+        conv(f'fnet.{nm}.0', a, b)
+        conv(f'fnet.{nm}.2', b, c2)
+    conv('fnet.flow.0', 64, 32)
+    conv('fnet.flow.2', 32, 2)
+    conv('srnet.conv_in.0', (scale * scale + 1) * in_nc, nf)
+    for i in range(nb):
+        conv(f'srnet.resblocks.{i}.conv.0', nf, nf)
+        conv(f'srnet.resblocks.{i}.conv.2', nf, nf)
+    for u in range(2 if scale == 4 else 1):
+        shapes[f'srnet.conv_up.{2 * u}.weight'] = (nf, nf, 3, 3)  # ConvT: [Cin,Cout,kH,kW]
+        shapes[f'srnet.conv_up.{2 * u}.bias'] = (nf,)
+    conv('srnet.conv_out', nf, out_nc)
+    if degradation == 'BD':
+        shapes['srnet.upsample_func.kernels'] = (scale, 4)
+    return shapes
+
+
+def make_frnet_params(seed=0, in_nc=3, out_nc=3, nf=64, nb=10, scale=4, degradation='BD',
+                      gain=1.0):
+    """Seeded weights, U(-b, b) with b = gain/sqrt(fan_in) like PyTorch's default
+    conv init (what codes/main.py:227-228 profiles with; no checkpoint is loaded).
+    numpy PCG64 stream -> identical on every box."""
+    rng = np.random.default_rng(seed)
+    p = OrderedDict()
+    for name, shp in frnet_param_shapes(in_nc, out_nc, nf, nb, scale, degradation).items():
+        if name.endswith('kernels'):
+            p[name] = _t(K.bicubic_kernels(scale))
+            continue
+        if name.endswith('.weight'):
+            if 'conv_up' in name:
+                fan_in = shp[1] * 9   # torch computes fan_in from dim 1 for ConvTranspose2d
+            else:
+                fan_in = shp[1] * 9
+            last_fan_in = fan_in
+        else:
+            fan_in = last_fan_in
+        b = gain / np.sqrt(fan_in)
+        p[name] = _t(rng.uniform(-b, b, size=shp).astype(np.float32))
+    return p
+
+
+def make_clip(seed, t, c, h, w, shift=1):
+    """Smooth translating pattern: bicubic-upsampled seeded noise
+    shifted `shift` px per frame, values in [0,1]."""
+    rng = np.random.default_rng(seed)
+    gh, gw = h // 4 + 4, (w + shift * t) // 4 + 4
+    base = rng.uniform(0.0, 1.0, size=(1, c, gh, gw)).astype(np.float32)
+    big = np.clip(K.bicubic_upsample(base, 4), 0.0, 1.0)
+    frames = [big[0, :, 2:2 + h, 2 + shift * i:2 + shift * i + w] for i in range(t)]
+    return _t(np.stack(frames).astype(np.float32))

@@ -1,0 +1,133 @@
+"""CPU: pin the oracle (oracle/) against outputs of the UNMODIFIED reference.
+
+The fixtures in tests/golden were written by oracle/gen_golden.py, which imports
+/root/reference and runs it on seeded inputs.  When /root/reference is present
+(build container) the oracle is additionally compared with the live reference at
+the BASELINE size 3x134x320.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ops_oracle as K
+from oracle import frnet_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def rand(seed, *shape, lo=0.0, hi=1.0):
+    return torch.from_numpy(np.random.default_rng(seed).uniform(lo, hi, size=shape).astype(np.float32))
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+# ------------------------------------------------------------------ functional ops
+def test_ops_against_reference_outputs():
+    g = np.load(os.path.join(G, 'ops.npz'))
+    x = rand(20, 2, 3, 20, 24).numpy()
+    flow = rand(21, 2, 2, 20, 24, lo=-4.0, hi=4.0).numpy()
+    flow[0, :, 0, 0] = [-30.0, 40.0]
+    w = K.backward_warp(x, flow)
+    assert np.abs(w - g['warped']).max() <= 2e-6          # fp32 sampling
+    w2 = K.backward_warp(x, flow, exact_reference_grid=False)
+    assert np.abs(w2 - g['warped']).max() <= 2e-5         # closed form x+u: ~1e-4 px of fp32 rounding
+    # pure index permutations: bit exact
+    assert np.array_equal(K.space_to_depth(rand(22, 2, 3, 16, 24).numpy(), 4), g['s2d4'])
+    assert np.array_equal(K.space_to_depth(rand(22, 2, 3, 16, 24).numpy(), 2), g['s2d2'])
+    xs = rand(23, 1, 3, 9, 11).numpy()
+    assert np.abs(K.bicubic_upsample(xs, 4) - g['bic4']).max() <= 1e-6
+    assert np.abs(K.bicubic_upsample(xs, 2) - g['bic2']).max() <= 1e-6
+    assert np.abs(K.bilinear_upsample(xs, 4) - g['bil4']).max() <= 1e-6
+    assert np.abs(K.bilinear_upsample(xs, 2) - g['bil2']).max() <= 1e-6
+    # uint8 quantisation incl. x.5 ties (round-half-even): bit exact
+    assert np.array_equal(K.float32_to_uint8(g['q_in']), g['q'])
+    # ConvTranspose2d(3,2,1,op=1) == 4 parity sub-convs interleaved (pixel-shuffle)
+    wt = rand(25, 8, 8, 3, 3, lo=-1, hi=1).numpy()
+    bt = rand(26, 8, lo=-1, hi=1).numpy()
+    ct = K.conv_transpose3x3s2_parity(rand(27, 1, 8, 5, 7).numpy(), wt, bt)
+    assert np.abs(ct - g['convt']).max() <= 5e-6
+
+
+def test_bicubic_kernel_values():
+    k = K.bicubic_kernels(4)
+    assert np.array_equal(k[0], np.array([0, 1, 0, 0], np.float32))
+    assert np.array_equal(k[1], np.array([-0.10546875, 0.87890625, 0.26171875, -0.03515625], np.float32))
+    assert np.array_equal(k[2], np.array([-0.09375, 0.59375, 0.59375, -0.09375], np.float32))
+    assert np.array_equal(K.bicubic_kernels(2), k[[0, 2]])
+
+
+# ------------------------------------------------------------------ FRNet.step
+@pytest.mark.parametrize('tag,gain', [('g1', 1.0), ('g2', 2.0)])
+def test_step_bd4(tag, gain):
+    g = np.load(os.path.join(G, f'step_bd4_18x28_{tag}.npz'))
+    p = O.make_frnet_params(11, scale=4, degradation='BD', gain=gain)
+    lr_curr, lr_prev, hr_prev = rand(1, 1, 3, 18, 28), rand(2, 1, 3, 18, 28), rand(3, 1, 3, 72, 112)
+    taps = {}
+    hr = O.frnet_step(p, lr_curr, lr_prev, hr_prev, 4, 'BD', taps=taps)
+    assert taps['lr_flow'].shape == (1, 2, 16, 24)         # 8*floor(h/8)
+    assert relerr(taps['lr_flow'].numpy(), g['lr_flow']) <= 2e-5
+    assert relerr(hr.numpy(), g['hr_curr']) <= 2e-5
+
+
+def test_step_bi2():
+    g = np.load(os.path.join(G, 'step_bi2_20x24_g2.npz'))
+    p = O.make_frnet_params(12, scale=2, degradation='BI', gain=2.0)
+    assert 'upsample_func.kernels' not in p and 'srnet.conv_up.2.weight' not in p
+    assert p['srnet.conv_in.0.weight'].shape == (64, 15, 3, 3)
+    hr = O.frnet_step(p, rand(4, 1, 3, 20, 24), rand(5, 1, 3, 20, 24), rand(6, 1, 3, 40, 48), 2, 'BI')
+    assert relerr(hr.numpy(), g['hr_curr']) <= 2e-5
+
+
+def test_infer_sequence_uint8():
+    g = np.load(os.path.join(G, 'infer_seq_bd4_16x24_g2.npz'))
+    p = O.make_frnet_params(13, scale=4, degradation='BD', gain=2.0)
+    seq = O.frnet_infer_sequence(p, O.make_clip(7, 4, 3, 16, 24), 4, 'BD')
+    assert seq.shape == g['hr_seq'].shape and seq.dtype == np.uint8
+    d = np.abs(seq.astype(np.int32) - g['hr_seq'].astype(np.int32))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3       # fp32 reassociation can flip a .5 tie
+
+
+def test_forward_sequence():
+    g = np.load(os.path.join(G, 'fwd_seq_bd4_16x16_g2.npz'))
+    p = O.make_frnet_params(14, scale=4, degradation='BD', gain=2.0)
+    d = O.frnet_forward_sequence(p, rand(8, 1, 3, 3, 16, 16), 4, 'BD')
+    for k in ('hr_data', 'hr_flow', 'lr_prev', 'lr_curr', 'lr_flow'):
+        assert tuple(d[k].shape) == g[k].shape, k
+        assert relerr(d[k].numpy(), g[k]) <= 3e-5, k
+
+
+def test_state_dict_layout_matches_reference_counts():
+    # BD 4x = 78 entries (76 params + 2 kernels buffers); BI 4x = 76
+    assert len(O.frnet_param_shapes(scale=4, degradation='BD')) == 78
+    assert len(O.frnet_param_shapes(scale=4, degradation='BI')) == 76
+    n = sum(int(np.prod(s)) for k, s in O.frnet_param_shapes(scale=4, degradation='BI').items())
+    assert n == 2589093
+
+
+# ------------------------------------------------------------------ live reference (build container only)
+@pytest.mark.skipif(not os.path.isdir('/root/reference/codes'), reason='reference not mounted')
+def test_oracle_vs_live_reference_full_size():
+    R = '/root/reference/codes'
+    if R not in sys.path:
+        sys.path.insert(0, R)
+    m = types.ModuleType('metrics')
+    m.__path__ = [R + '/metrics']
+    sys.modules.setdefault('metrics', m)
+    from models.networks.tecogan_nets import FRNet
+    net = FRNet(3, 3, 64, 10, 'BD', 4)
+    p = O.make_frnet_params(5, gain=2.0)
+    net.load_state_dict(p, strict=True)
+    net.eval()
+    lr_curr, lr_prev, hr_prev = rand(1, 1, 3, 134, 320), rand(2, 1, 3, 134, 320), rand(3, 1, 3, 536, 1280)
+    with torch.no_grad():
+        ref = net.step(lr_curr, lr_prev, hr_prev)
+    hr = O.frnet_step(p, lr_curr, lr_prev, hr_prev, 4, 'BD')
+    assert relerr(hr.numpy(), ref.numpy()) <= 5e-5

@@ -1,0 +1,642 @@
+// 3x3 convolution / stride-2 transposed convolution as a persistent, warp-specialised tcgen05
+// implicit GEMM for sm_100a.
+//
+//   M tile  = 128 output pixels = a 16x8 patch of one image (TMEM lane m <-> pixel (m>>3, m&7))
+//   N       = cout (16 / 64 / 128 / 256), one UMMA covers the whole N
+//   K       = 64-channel chunks x 9 taps; UMMA K = 16 -> 4 MMAs per (tap, chunk)
+//   A       : NHWC fp16 activations, fetched by TMA (4-D tiled map, 128B swizzle, OOB zero fill =
+//             the conv's zero padding) either as ONE halo box (18x10 px) per (tile, chunk) whose
+//             nine shifted views are addressed through the UMMA descriptor (start address +=
+//             (dy*10+dx)*128 B, 8-row-group stride = 10*128 B), or as one 16x8 box per tap.
+//   B       : weights pre-packed on the device in the exact swizzled smem image
+//             (tg_pack_*_weights), either resident in smem for the whole kernel (SRNet, thin
+//             FNet layers) or streamed per (tap, chunk) with cp.async.bulk (fat FNet layers).
+//   D       : fp32 accumulators in TMEM, double buffered (epilogue of tile i overlaps the MMAs of
+//             tile i+1).  The transposed conv keeps 4 parity accumulators (1/2/2/4 taps) and
+//             stores them through 4 strided tensor maps = the pixel-shuffle interleave.
+//   roles   : warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
+//             warps 4..11 = epilogue (tcgen05.ld -> bias/act/residual -> fp16 -> swizzled smem
+//             -> TMA store; or the fused tanh*24 / bicubic-residual NCHW fp32 epilogues).
+//
+// Replaces the nn.Conv2d / nn.ConvTranspose2d library calls K1, K10, K11, K12 of SURVEY.md 2.1.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "tg_common.cuh"
+#include "tg_epilogue.cuh"
+
+namespace {
+
+constexpr int TH = 16, TW = 8;
+constexpr int kThreads = 384;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kHeaderBytes = 2048;   // barriers + tmem ptr (first 1 KB) + bias (second 1 KB)
+constexpr uint32_t kTapABytes = TH * TW * 128;  // 16 KB
+constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in limit per CTA
+
+struct KParams {
+  tg_conv_desc d;
+  int tiles_x, tiles_y, num_tiles;
+  int chunks, n_acc;
+  int halo, b_resident;
+  int box_w, box_h, org_x, org_y;
+  int n_stages;
+  uint32_t stage_bytes, a_bytes, b_tile_bytes;
+  uint32_t off_b, off_stage, off_staging;
+  uint32_t idesc;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug must fault, never hang the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 3000000000LL) {
+      printf("tg_conv_tcgen05: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+             blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes,
+                                          uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2,
+                                             int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; kind::f16, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128B swizzle (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 = byte
+// stride between 8-row groups | [46,48) version=1 | [61,64) layout=2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo_bytes) {
+  uint64_t d = static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+struct TileCoord { int n, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
+  TileCoord t;
+  const int per_img = p.tiles_x * p.tiles_y;
+  t.n = tile / per_img;
+  const int r = tile - t.n * per_img;
+  t.y0 = (r / p.tiles_x) * TH;
+  t.x0 = (r % p.tiles_x) * TW;
+  return t;
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
+                    const __grid_constant__ CUtensorMap map_y0,
+                    const __grid_constant__ CUtensorMap map_y1,
+                    const __grid_constant__ CUtensorMap map_y2,
+                    const __grid_constant__ CUtensorMap map_y3, const KParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
+  uint8_t* sm = smem_raw + (base - raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const tg_conv_desc& d = p.d;
+
+  // header: barriers
+  const uint32_t bar_full = base;                       // [kMaxStages]
+  const uint32_t bar_empty = base + 8 * kMaxStages;     // [kMaxStages]
+  const uint32_t bar_tfull = base + 16 * kMaxStages;    // [2]
+  const uint32_t bar_tempty = bar_tfull + 16;           // [2]
+  const uint32_t bar_b = bar_tempty + 16;               // [1]
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 48);
+  float* bias_s = reinterpret_cast<float*>(sm + 1024);
+
+  const int epi_warps_active = (d.cout >= 64) ? 8 : 4;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    if (d.epilogue == TG_EPI_NHWC_F16) {
+      tma_prefetch_desc(&map_y0);
+      if (p.n_acc == 4) { tma_prefetch_desc(&map_y1); tma_prefetch_desc(&map_y2); tma_prefetch_desc(&map_y3); }
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.n_stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1);
+      mbar_init(bar_tempty + 8 * b, epi_warps_active);
+    }
+    mbar_init(bar_b, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
+  for (int i = threadIdx.x; i < d.cout; i += kThreads) bias_s[i] = d.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const uint32_t smem_b = base + p.off_b;
+  const uint32_t smem_stage0 = base + p.off_stage;
+  const unsigned char* wglob = reinterpret_cast<const unsigned char*>(d.weights);
+  const int n_tiles_w = 9 * p.chunks;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      if (p.b_resident) {
+        mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_tile_bytes);
+        for (int t = 0; t < n_tiles_w; ++t)
+          bulk_load(smem_b + t * p.b_tile_bytes, wglob + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, bar_b);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord tc = tile_coord(p, tile);
+        if (p.halo) {
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+            mbar_expect_tx(bar_full + 8 * stage, p.a_bytes);
+            tma_load_4d(smem_stage0 + stage * p.stage_bytes, &map_a, bar_full + 8 * stage, c * 64,
+                        tc.x0 + p.org_x, tc.y0 + p.org_y, tc.n);
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          for (int g = 0; g < 9; ++g) {
+            const TgGroup gr = tg_group(d.kind, g);
+            for (int c = 0; c < p.chunks; ++c) {
+              mbar_wait(bar_empty + 8 * stage, phase ^ 1, 2);
+              const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
+              mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + (p.b_resident ? 0u : p.b_tile_bytes));
+              tma_load_4d(sa, &map_a, bar_full + 8 * stage, c * 64, tc.x0 + gr.dx, tc.y0 + gr.dy, tc.n);
+              if (!p.b_resident)
+                bulk_load(sa + kTapABytes, wglob + (size_t)(g * p.chunks + c) * p.b_tile_bytes,
+                          p.b_tile_bytes, bar_full + 8 * stage);
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer (single thread)
+    if (lane == 0) {
+      if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const uint32_t acc_stride = (uint32_t)(p.n_acc * d.cout);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + buf * acc_stride;
+        uint32_t written = 0;   // bit a: accumulator a already holds a partial sum
+        if (p.halo) {
+          const uint32_t sbo = (uint32_t)p.box_w * 128u;
+          for (int c = 0; c < p.chunks; ++c) {
+            mbar_wait(bar_full + 8 * stage, phase, 5);
+            tc_fence_after();
+            const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
+            for (int g = 0; g < 9; ++g) {
+              const TgGroup gr = tg_group(d.kind, g);
+              const uint32_t a_addr = sa + (uint32_t)((gr.dy - p.org_y) * p.box_w + (gr.dx - p.org_x)) * 128u;
+              const uint32_t b_addr = smem_b + (uint32_t)(g * p.chunks + c) * p.b_tile_bytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(d_base + gr.acc * d.cout, make_sdesc(a_addr + k * 32, sbo),
+                         make_sdesc(b_addr + k * 32, 1024), p.idesc, (written >> gr.acc) & 1u);
+                written |= 1u << gr.acc;
+              }
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          for (int g = 0; g < 9; ++g) {
+            const TgGroup gr = tg_group(d.kind, g);
+            for (int c = 0; c < p.chunks; ++c) {
+              mbar_wait(bar_full + 8 * stage, phase, 6);
+              tc_fence_after();
+              const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
+              const uint32_t b_addr = p.b_resident
+                                          ? smem_b + (uint32_t)(g * p.chunks + c) * p.b_tile_bytes
+                                          : sa + kTapABytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16(d_base + gr.acc * d.cout, make_sdesc(sa + k * 32, 1024),
+                         make_sdesc(b_addr + k * 32, 1024), p.idesc, (written >> gr.acc) & 1u);
+                written |= 1u << gr.acc;
+              }
+              umma_commit(bar_empty + 8 * stage);
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue
+    const int ew = warp - 4;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = ew >> 2;      // column half
+    const bool active = (d.cout >= 64) || half == 0;
+    const int cols_per_half = (d.cout >= 64) ? d.cout / 2 : d.cout;
+    const int r = q * 32 + lane;   // row of the tile = TMEM lane
+    const int ty = r >> 3, tx = r & 7;
+    const uint32_t acc_stride = (uint32_t)(p.n_acc * d.cout);
+    const int chunks_out = d.cout / 64;
+    const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      const TileCoord tc = tile_coord(p, tile);
+      const int py = tc.y0 + ty, px = tc.x0 + tx;
+      const bool inb = py < d.h && px < d.w;
+      if (d.epilogue == TG_EPI_NHWC_F16) {
+        if (ew == 0 && lane == 0) bulk_wait_read0();   // staging of the previous tile drained
+        named_bar_sync(1, 256);
+      }
+      if (active) {
+        mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+        tc_fence_after();
+        if (d.epilogue == TG_EPI_NHWC_F16) {
+          const int pieces = cols_per_half / 32;
+          for (int acc = 0; acc < p.n_acc; ++acc) {
+            for (int pc = 0; pc < pieces; ++pc) {
+              const int col0 = half * cols_per_half + pc * 32;
+              uint32_t v[32];
+              tmem_ld32(tmem_base + buf * acc_stride + acc * d.cout + col0 + ((uint32_t)(q * 32) << 16), v);
+              uint4 res[4];
+              const bool has_res = (d.residual != nullptr) && inb;
+              if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const __half*>(d.residual) +
+                    (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+              }
+              tmem_ld_wait();
+              if (acc == p.n_acc - 1 && pc == pieces - 1) {
+                // all TMEM reads of this warp for this buffer are done -> hand it back to the MMA
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+              }
+              uint8_t* srow = sm + p.off_staging + (size_t)(acc * chunks_out + (col0 >> 6)) * 16384 + r * 128;
+              const int cbase = (col0 & 63) >> 3;   // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                __align__(16) __half2 o[4];
+                const __half2* rh = reinterpret_cast<const __half2*>(&res[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int cidx = i * 8 + j * 2;
+                  float a0 = tg_epi_val(__uint_as_float(v[cidx]), bias_s[col0 + cidx], d.act);
+                  float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bias_s[col0 + cidx + 1], d.act);
+                  if (has_res) {
+                    const float2 rf = __half22float2(rh[j]);
+                    a0 += rf.x; a1 += rf.y;
+                  }
+                  o[j] = __floats2half2_rn(a0, a1);
+                }
+                *reinterpret_cast<uint4*>(srow + (((cbase + i) ^ (r & 7)) << 4)) =
+                    *reinterpret_cast<const uint4*>(o);
+              }
+            }
+          }
+        } else {
+          // NCHW fp32 epilogues: cout == 16, only the first cout_real columns are real
+          uint32_t v[16];
+          tmem_ld16(tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          if (inb) {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
+              else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
+            }
+          }
+        }
+      }
+      if (d.epilogue == TG_EPI_NHWC_F16) {
+        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA store
+        named_bar_sync(1, 256);
+        if (ew == 0 && lane == 0) {
+          for (int acc = 0; acc < p.n_acc; ++acc)
+            for (int cc = 0; cc < chunks_out; ++cc)
+              tma_store_4d(ymaps[acc], base + p.off_staging + (uint32_t)(acc * chunks_out + cc) * 16384u,
+                           cc * 64, tc.x0, tc.y0, tc.n);
+          bulk_commit();
+        }
+      }
+    }
+    if (d.epilogue == TG_EPI_NHWC_F16 && ew == 0 && lane == 0) bulk_wait0();
+  }
+
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// NHWC fp16 tensor [n][h][w][c] with explicit element strides for w/h/n (convT parity views)
+int encode_nhwc(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, size_t sw, size_t sh,
+                size_t sn, int box_c, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_REQUIRE(r == CUDA_SUCCESS, TG_E_DRIVER,
+             "cuTensorMapEncodeTiled failed (%d) c=%d w=%d h=%d n=%d box=%dx%dx%d", (int)r, c, w, h, n,
+             box_c, box_w, box_h);
+  return TG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tg_conv_validate(const tg_conv_desc* d, const char* who) {
+  TG_REQUIRE(d != nullptr, TG_E_INVALID, "%s: null descriptor", who);
+  TG_REQUIRE(d->x && d->weights && d->bias && d->y, TG_E_INVALID, "%s: null pointer", who);
+  TG_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, TG_E_INVALID, "%s: bad size n=%d h=%d w=%d", who, d->n, d->h, d->w);
+  TG_REQUIRE(d->kind == TG_CONV_3X3 || d->kind == TG_CONVT_3X3_S2, TG_E_INVALID, "%s: kind", who);
+  TG_REQUIRE(d->act >= TG_ACT_NONE && d->act <= TG_ACT_LRELU02, TG_E_INVALID, "%s: act", who);
+  TG_REQUIRE(d->cin == 64 || d->cin == 128 || d->cin == 256, TG_E_UNSUPPORTED,
+             "%s: cin=%d (stored channels must be 64, 128 or 256)", who, d->cin);
+  if (d->epilogue == TG_EPI_NHWC_F16) {
+    TG_REQUIRE(d->cout == 64 || d->cout == 128 || d->cout == 256, TG_E_UNSUPPORTED,
+               "%s: cout=%d (64, 128 or 256 for the NHWC epilogue)", who, d->cout);
+    TG_REQUIRE(!(d->residual && d->kind != TG_CONV_3X3), TG_E_UNSUPPORTED, "%s: residual with convT", who);
+    TG_REQUIRE(!(d->kind == TG_CONVT_3X3_S2 && d->cout != 64), TG_E_UNSUPPORTED,
+               "%s: convT needs cout == 64 (4 parity accumulators in TMEM)", who);
+  } else if (d->epilogue == TG_EPI_FLOW_NCHW_F32 || d->epilogue == TG_EPI_OUT_NCHW_F32) {
+    TG_REQUIRE(d->kind == TG_CONV_3X3 && d->cout == 16 && d->cout_real >= 1 && d->cout_real <= 4,
+               TG_E_UNSUPPORTED, "%s: NCHW epilogues need conv3x3, cout=16, cout_real<=4", who);
+    TG_REQUIRE(d->residual == nullptr, TG_E_UNSUPPORTED, "%s: residual with NCHW epilogue", who);
+    if (d->epilogue == TG_EPI_OUT_NCHW_F32) {
+      TG_REQUIRE(d->aux != nullptr, TG_E_INVALID, "%s: aux (lr_curr) is null", who);
+      TG_REQUIRE((d->up_scale == 2 || d->up_scale == 4) && d->h % d->up_scale == 0 &&
+                     d->w % d->up_scale == 0, TG_E_INVALID, "%s: up_scale", who);
+      TG_REQUIRE(d->up_mode == TG_UP_BICUBIC || d->up_mode == TG_UP_BILINEAR, TG_E_INVALID, "%s: up_mode", who);
+    }
+  } else {
+    TG_REQUIRE(false, TG_E_INVALID, "%s: epilogue %d", who, d->epilogue);
+  }
+  return TG_OK;
+}
+
+int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
+  int rc = tg_conv_validate(d, "conv_tcgen05");
+  if (rc != TG_OK) return rc;
+  TG_REQUIRE(d->a_mode >= TG_AMODE_AUTO && d->a_mode <= TG_AMODE_TAP, TG_E_INVALID, "conv_tcgen05: a_mode");
+  TG_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->weights & 15) == 0 && ((uintptr_t)d->y & 15) == 0,
+             TG_E_INVALID, "conv_tcgen05: pointers must be 16-byte aligned");
+
+  KParams p;
+  p.d = *d;
+  p.tiles_x = tg_ceil_div(d->w, TW);
+  p.tiles_y = tg_ceil_div(d->h, TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * d->n;
+  p.chunks = d->cin / 64;
+  p.n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
+  p.b_tile_bytes = (uint32_t)d->cout * 128u;
+  p.idesc = (1u << 4) | ((uint32_t)(d->cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  const uint32_t b_total = 9u * p.chunks * p.b_tile_bytes;
+  const uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? (uint32_t)p.n_acc * (d->cout / 64) * 16384u : 0u;
+  const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
+  const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
+  const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
+  const uint32_t halo_stage = (halo_bytes + 1023u) & ~1023u;
+  const uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
+
+  const bool can_resident_halo = fixed + b_total + 2u * halo_stage <= kSmemLimit;
+  const bool can_resident_tap = fixed + b_total + 2u * kTapABytes <= kSmemLimit;
+  int mode = d->a_mode;
+  if (mode == TG_AMODE_AUTO) mode = can_resident_halo ? TG_AMODE_HALO : TG_AMODE_TAP;
+  TG_REQUIRE(!(mode == TG_AMODE_HALO && !can_resident_halo), TG_E_UNSUPPORTED,
+             "conv_tcgen05: halo mode needs the weights resident in smem (cin=%d cout=%d)", d->cin, d->cout);
+  p.halo = mode == TG_AMODE_HALO;
+  p.b_resident = p.halo ? 1 : (can_resident_tap ? 1 : 0);
+  if (p.halo) {
+    p.box_w = hbox_w; p.box_h = hbox_h;
+    p.org_x = d->kind == TG_CONV_3X3 ? -1 : 0;
+    p.org_y = p.org_x;
+    p.a_bytes = halo_bytes;
+    p.stage_bytes = halo_stage;
+  } else {
+    p.box_w = TW; p.box_h = TH; p.org_x = 0; p.org_y = 0;
+    p.a_bytes = kTapABytes;
+    p.stage_bytes = kTapABytes + (p.b_resident ? 0u : p.b_tile_bytes);
+  }
+  const uint32_t avail = kSmemLimit - fixed - (p.b_resident ? b_total : 0u);
+  int stages = (int)(avail / p.stage_bytes);
+  const int want = p.halo ? 4 : kMaxStages;
+  if (stages > want) stages = want;
+  TG_REQUIRE(stages >= 2, TG_E_UNSUPPORTED, "conv_tcgen05: shared memory budget (cin=%d cout=%d)", d->cin, d->cout);
+  p.n_stages = stages;
+  p.off_b = kHeaderBytes;
+  p.off_stage = kHeaderBytes + (p.b_resident ? b_total : 0u);
+  p.off_staging = p.off_stage + (uint32_t)stages * p.stage_bytes;
+  const uint32_t smem_bytes = 1024u + p.off_staging + staging;
+  TG_REQUIRE(smem_bytes <= kSmemLimit, TG_E_UNSUPPORTED, "conv_tcgen05: smem %u > limit", smem_bytes);
+
+  // tensor maps
+  CUtensorMap map_a, map_y[4];
+  rc = encode_nhwc(&map_a, d->x, d->cin, d->w, d->h, d->n, (size_t)d->cin, (size_t)d->w * d->cin,
+                   (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
+  if (rc != TG_OK) return rc;
+  if (d->epilogue == TG_EPI_NHWC_F16) {
+    if (d->kind == TG_CONV_3X3) {
+      rc = encode_nhwc(&map_y[0], d->y, d->cout, d->w, d->h, d->n, (size_t)d->cout, (size_t)d->w * d->cout,
+                       (size_t)d->h * d->w * d->cout, 64, TW, TH);
+      if (rc != TG_OK) return rc;
+      map_y[1] = map_y[2] = map_y[3] = map_y[0];
+    } else {
+      const size_t OW = 2 * (size_t)d->w, OH = 2 * (size_t)d->h;
+      for (int a = 0; a < 4; ++a) {
+        const int py = a >> 1, px = a & 1;
+        const __half* yb = reinterpret_cast<const __half*>(d->y) + ((size_t)py * OW + px) * d->cout;
+        rc = encode_nhwc(&map_y[a], yb, d->cout, d->w, d->h, d->n, 2 * (size_t)d->cout, 2 * OW * d->cout,
+                         OH * OW * d->cout, 64, TW, TH);
+        if (rc != TG_OK) return rc;
+      }
+    }
+  } else {
+    map_y[0] = map_y[1] = map_y[2] = map_y[3] = map_a;   // unused
+  }
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kSmemLimit);
+  });
+  TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_tcgen05: cudaFuncSetAttribute: %s",
+             cudaGetErrorString(attr_err));
+
+  int sms = 0;
+  rc = tg_device_sm_count(&sms);
+  if (rc != TG_OK) return rc;
+  int grid = d->max_ctas > 0 ? d->max_ctas : sms;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
+  // allocation can never contend
+  conv_tcgen05_kernel<<<grid, kThreads, kSmemLimit, (cudaStream_t)stream>>>(map_a, map_y[0], map_y[1],
+                                                                           map_y[2], map_y[3], p);
+  TG_CUDA_LAUNCH_CHECK("conv_tcgen05");
+  return TG_OK;
+}
+
+}  // extern "C"

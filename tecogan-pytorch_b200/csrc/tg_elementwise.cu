@@ -1,0 +1,454 @@
+// HBM-bound kernels of the FRNet hot path: fused warp + space_to_depth + concat, FNet's
+// pool / x2-upsample, layout packs, module-boundary NCHW fp32 ops, uint8 quantisation.
+// Reference call sites are cited per entry point in include/tecogan_b200.h.
+#include "tg_common.cuh"
+
+namespace {
+
+// =====================================================================================
+// fused backward_warp + space_to_depth + concat
+//
+// One CTA produces the SRNet input of LRW = 128/S consecutive LR pixels of one LR row:
+//   - 128 threads = 128 consecutive HR columns; each thread walks the S HR rows of the
+//     LR row (flow reads are 512-byte coalesced row segments per plane, the 4-corner
+//     gathers of hr_prev stay within a few 128B lines because the flow is smooth),
+//   - results are transposed through shared memory into NHWC pixels (cpad fp16 each) so
+//     the CTA stores one contiguous LRW*cpad*2-byte run with 16-byte vectors.
+// Warp arithmetic follows net_utils.py:50-82 in closed form: sample at (X+u, Y+v), clamp to
+// the border, x1=min(x0+1,W-1)  (SURVEY.md 8-a4).
+// =====================================================================================
+template <int S>
+struct WarpTile {
+  static constexpr int kThreads = 128;
+  static constexpr int kLrw = kThreads / S;
+};
+
+__device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, int H, int W,
+                                               float fx, float fy) {
+  fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+  fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+  const float x0f = floorf(fx), y0f = floorf(fy);
+  const int x0 = (int)x0f, y0 = (int)y0f;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float ax = fx - x0f, ay = fy - y0f;
+  const float* r0 = plane + (size_t)y0 * W;
+  const float* r1 = plane + (size_t)y1 * W;
+  const float v00 = __ldg(r0 + x0), v01 = __ldg(r0 + x1);
+  const float v10 = __ldg(r1 + x0), v11 = __ldg(r1 + x1);
+  return v00 * (1.f - ax) * (1.f - ay) + v01 * ax * (1.f - ay) + v10 * (1.f - ax) * ay +
+         v11 * ax * ay;
+}
+
+template <int S, bool LRFLOW>
+__global__ void __launch_bounds__(128)
+warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
+                       const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
+                       int w, int h8, int w8, int up_mode, int cpad) {
+  constexpr int LRW = WarpTile<S>::kLrw;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* tile = reinterpret_cast<__half*>(smem_raw);  // [LRW][cpad]
+
+  const int t = threadIdx.x;
+  const int x0 = blockIdx.x * LRW;      // first LR column of the tile
+  const int y = blockIdx.y;             // LR row
+  const int n = blockIdx.z;
+  const int H = h * S, W = w * S;
+  const int X = x0 * S + t;             // HR column of this thread
+  const int lx = t / S, sx = t - lx * S;
+
+  // zero the pad channels [ (S*S+1)*C, cpad ) and stage lr_curr
+  const int used = (S * S + 1) * C;
+  for (int i = t; i < LRW * (cpad - used); i += 128) {
+    const int p = i / (cpad - used), k = i - p * (cpad - used);
+    tile[p * cpad + used + k] = __float2half(0.f);
+  }
+  for (int i = t; i < LRW * C; i += 128) {
+    const int k = i / LRW, p = i - k * LRW;
+    const int xx = x0 + p;
+    float v = 0.f;
+    if (xx < w) v = __ldg(lr_curr + (((size_t)n * C + k) * h + y) * w + xx);
+    tile[p * cpad + k] = __float2half(v);
+  }
+
+  if (X < W) {
+    float u[S], v[S];
+    if (LRFLOW) {
+      // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
+      const float* f0 = flow + ((size_t)n * 2 + 0) * h8 * w8;
+      const float* f1 = flow + ((size_t)n * 2 + 1) * h8 * w8;
+#pragma unroll
+      for (int sy = 0; sy < S; ++sy) {
+        u[sy] = (float)S * tg_upsample_at(f0, h8, w8, h, w, S, up_mode, y * S + sy, X);
+        v[sy] = (float)S * tg_upsample_at(f1, h8, w8, h, w, S, up_mode, y * S + sy, X);
+      }
+    } else {
+      const float* f0 = flow + (((size_t)n * 2 + 0) * H + (size_t)y * S) * W + X;
+      const float* f1 = flow + (((size_t)n * 2 + 1) * H + (size_t)y * S) * W + X;
+#pragma unroll
+      for (int sy = 0; sy < S; ++sy) {
+        u[sy] = __ldg(f0 + (size_t)sy * W);
+        v[sy] = __ldg(f1 + (size_t)sy * W);
+      }
+    }
+#pragma unroll
+    for (int sy = 0; sy < S; ++sy) {
+      const float fx = (float)X + u[sy];
+      const float fy = (float)(y * S + sy) + v[sy];
+      // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
+      __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
+      for (int k = 0; k < C; ++k) {
+        const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
+        dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+      }
+    }
+  }
+  __syncthreads();
+
+  // coalesced store of min(LRW, w-x0) pixels * cpad halves (cpad*2 bytes, multiple of 16)
+  const int npx = min(LRW, w - x0);
+  const int vec_per_px = cpad / 8;  // uint4 per pixel
+  const uint4* src = reinterpret_cast<const uint4*>(tile);
+  uint4* dstg = reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0) * cpad);
+  for (int i = t; i < npx * vec_per_px; i += 128) dstg[i] = src[i];
+}
+
+// =====================================================================================
+// FNet helpers on NHWC fp16 (8 channels = one 16-byte vector per thread)
+// =====================================================================================
+__global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
+                                  int w, int c8) {
+  const int ho = h / 2, wo = w / 2;
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % c8);
+    size_t p = i / c8;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int nn = (int)(p / ho);
+    const size_t base = (((size_t)nn * h + 2 * yo) * w + 2 * xo) * c8 + cv;
+    uint4 a = __ldg(x + base), b = __ldg(x + base + c8);
+    uint4 c = __ldg(x + base + (size_t)w * c8), d = __ldg(x + base + (size_t)w * c8 + c8);
+    uint4 r;
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    const __half2* ch = reinterpret_cast<const __half2*>(&c);
+    const __half2* dh = reinterpret_cast<const __half2*>(&d);
+    __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rh[k] = __hmax2(__hmax2(ah[k], bh[k]), __hmax2(ch[k], dh[k]));
+    y[i] = r;
+  }
+}
+
+// F.interpolate(scale_factor=2, bilinear, align_corners=False):
+// out[2i] = .25*in[max(i-1,0)] + .75*in[i], out[2i+1] = .75*in[i] + .25*in[min(i+1,L-1)]
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
+                                  int w, int c8) {
+  const int ho = 2 * h, wo = 2 * w;
+  const size_t total = (size_t)n * ho * wo * c8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % c8);
+    size_t p = i / c8;
+    const int xo = (int)(p % wo); p /= wo;
+    const int yo = (int)(p % ho);
+    const int nn = (int)(p / ho);
+    const int yi = yo >> 1, xi = xo >> 1;
+    const int ya = (yo & 1) ? yi : max(yi - 1, 0), yb = (yo & 1) ? min(yi + 1, h - 1) : yi;
+    const int xa = (xo & 1) ? xi : max(xi - 1, 0), xb = (xo & 1) ? min(xi + 1, w - 1) : xi;
+    // weights on (a,b): odd -> (.75,.25), even -> (.25,.75)
+    const float wya = (yo & 1) ? 0.75f : 0.25f, wxa = (xo & 1) ? 0.75f : 0.25f;
+    const float wyb = 1.f - wya, wxb = 1.f - wxa;
+    const size_t rowa = ((size_t)nn * h + ya) * w, rowb = ((size_t)nn * h + yb) * w;
+    const uint4 vaa = __ldg(x + (rowa + xa) * c8 + cv), vab = __ldg(x + (rowa + xb) * c8 + cv);
+    const uint4 vba = __ldg(x + (rowb + xa) * c8 + cv), vbb = __ldg(x + (rowb + xb) * c8 + cv);
+    const __half2* paa = reinterpret_cast<const __half2*>(&vaa);
+    const __half2* pab = reinterpret_cast<const __half2*>(&vab);
+    const __half2* pba = reinterpret_cast<const __half2*>(&vba);
+    const __half2* pbb = reinterpret_cast<const __half2*>(&vbb);
+    uint4 r;
+    __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 aa = __half22float2(paa[k]), ab = __half22float2(pab[k]);
+      const float2 ba = __half22float2(pba[k]), bb = __half22float2(pbb[k]);
+      float2 o;
+      o.x = wya * (wxa * aa.x + wxb * ab.x) + wyb * (wxa * ba.x + wxb * bb.x);
+      o.y = wya * (wxa * aa.y + wxb * ab.y) + wyb * (wxa * ba.y + wxb * bb.y);
+      rh[k] = __float22half2_rn(o);
+    }
+    y[i] = r;
+  }
+}
+
+// cat([x1,x2],1) + NCHW fp32 -> NHWC fp16 (cpad channels, zero padded). One thread per
+// (pixel, 8-channel vector); plane reads are coalesced across pixels.
+__global__ void pack_pair_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
+                                 uint4* __restrict__ y, int n, int c, int h, int w, int c8,
+                                 int c_offset, int zero_fill) {
+  const size_t hw = (size_t)h * w;
+  const size_t total = (size_t)n * hw * c8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    // pixel-fastest mapping inside a vector index so that plane loads coalesce
+    const size_t px = i % ((size_t)n * hw);
+    const int cv = (int)(i / ((size_t)n * hw));
+    const int nn = (int)(px / hw);
+    const size_t sp = px % hw;
+    __align__(16) __half vals[8];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = cv * 8 + k - c_offset;
+      float v = 0.f;
+      if (ch >= 0 && ch < c) { v = __ldg(x1 + ((size_t)nn * c + ch) * hw + sp); any = true; }
+      else if (x2 != nullptr && ch >= c && ch < 2 * c) {
+        v = __ldg(x2 + ((size_t)nn * c + (ch - c)) * hw + sp); any = true;
+      }
+      vals[k] = __float2half(v);
+    }
+    if (any || zero_fill) y[px * c8 + cv] = *reinterpret_cast<const uint4*>(vals);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int n,
+                                    int c, int h, int w, int cpad) {
+  const size_t hw = (size_t)h * w;
+  const size_t total = (size_t)n * c * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t sp = i % hw;
+    const int ch = (int)((i / hw) % c);
+    const int nn = (int)(i / (hw * c));
+    y[i] = __half2float(x[((size_t)nn * hw + sp) * cpad + ch]);
+  }
+}
+
+// =====================================================================================
+// module-boundary NCHW fp32 ops
+// =====================================================================================
+__global__ void backward_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow,
+                                     float* __restrict__ y, int n, int c, int h, int w) {
+  const size_t hw = (size_t)h * w;
+  const size_t total = (size_t)n * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int nn = (int)(i / hw);
+    const size_t sp = i % hw;
+    const int yy = (int)(sp / w), xx = (int)(sp % w);
+    const float fx = (float)xx + __ldg(flow + ((size_t)nn * 2 + 0) * hw + sp);
+    const float fy = (float)yy + __ldg(flow + ((size_t)nn * 2 + 1) * hw + sp);
+    for (int k = 0; k < c; ++k)
+      y[((size_t)nn * c + k) * hw + sp] = bilerp_border(x + ((size_t)nn * c + k) * hw, h, w, fx, fy);
+  }
+}
+
+__global__ void space_to_depth_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
+                                      int c, int h, int w, int s) {
+  const int oh = h / s, ow = w / s;
+  const size_t total = (size_t)n * c * s * s * oh * ow;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t p = i;
+    const int xo = (int)(p % ow); p /= ow;
+    const int yo = (int)(p % oh); p /= oh;
+    const int oc = (int)(p % (c * s * s));
+    const int nn = (int)(p / (c * s * s));
+    const int k = oc % c, blk = oc / c, sy = blk / s, sx = blk % s;
+    y[i] = __ldg(x + (((size_t)nn * c + k) * h + (yo * s + sy)) * w + (xo * s + sx));
+  }
+}
+
+__global__ void upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int nc,
+                                     int hin, int win, int h, int w, int s, int up_mode,
+                                     float mul) {
+  const int H = h * s, W = w * s;
+  const size_t total = (size_t)nc * H * W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const int Y = (int)((i / W) % H);
+    const size_t pl = i / ((size_t)H * W);
+    y[i] = mul * tg_upsample_at(x + pl * hin * win, hin, win, h, w, s, up_mode, Y, X);
+  }
+}
+
+// float32_to_uint8 + CHW->HWC: uint8(clip(rint(x*255),0,255)), rint = round-half-even
+__global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, int c,
+                                int h, int w) {
+  const size_t hw = (size_t)h * w;
+  const size_t total = (size_t)n * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int nn = (int)(i / hw);
+    const size_t sp = i % hw;
+    for (int k = 0; k < c; ++k) {
+      const float v = __ldg(x + ((size_t)nn * c + k) * hw + sp) * 255.f;
+      const float r = fminf(fmaxf(rintf(v), 0.f), 255.f);
+      y[i * c + k] = (uint8_t)r;
+    }
+  }
+}
+
+inline int grid_for(size_t total, int block) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+static int warp_launch(const float* hr_prev, const float* flow, const float* lr_curr, void* out,
+                       int n, int c, int h, int w, int h8, int w8, int s, int up_mode, int cpad,
+                       bool lrflow, void* stream) {
+  TG_REQUIRE(hr_prev && flow && lr_curr && out, TG_E_INVALID, "warp_s2d_concat: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "warp_s2d_concat: bad size");
+  TG_REQUIRE(s == 2 || s == 4, TG_E_UNSUPPORTED, "warp_s2d_concat: scale %d (2 or 4)", s);
+  TG_REQUIRE(cpad % 8 == 0 && (s * s + 1) * c <= cpad, TG_E_UNSUPPORTED,
+             "warp_s2d_concat: (s*s+1)*c=%d does not fit cpad=%d", (s * s + 1) * c, cpad);
+  TG_REQUIRE(n <= 65535 && h <= 65535, TG_E_UNSUPPORTED, "warp_s2d_concat: grid too large");
+  if (lrflow) {
+    TG_REQUIRE(h8 > 0 && w8 > 0 && h8 <= h && w8 <= w && (h - h8) < h8 && (w - w8) < w8,
+               TG_E_INVALID, "warp_s2d_concat: bad reflect pad %dx%d -> %dx%d", h8, w8, h, w);
+    TG_REQUIRE(up_mode == TG_UP_BICUBIC || up_mode == TG_UP_BILINEAR, TG_E_INVALID,
+               "warp_s2d_concat: up_mode");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lrw = 128 / s;
+  dim3 grid(tg_ceil_div(w, lrw), h, n);
+  const size_t smem = (size_t)lrw * cpad * sizeof(__half);
+  __half* o = (__half*)out;
+  if (s == 4) {
+    if (lrflow) warp_s2d_concat_kernel<4, true><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<4, false><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+  } else {
+    if (lrflow) warp_s2d_concat_kernel<2, true><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<2, false><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+  }
+  TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
+  return TG_OK;
+}
+
+int tg_warp_s2d_concat_hrflow(const float* hr_prev, const float* hr_flow, const float* lr_curr,
+                              void* out, int n, int c, int h, int w, int s, int cpad,
+                              void* stream) {
+  return warp_launch(hr_prev, hr_flow, lr_curr, out, n, c, h, w, 0, 0, s, 0, cpad, false, stream);
+}
+
+int tg_warp_s2d_concat_lrflow(const float* hr_prev, const float* lr_flow, const float* lr_curr,
+                              void* out, int n, int c, int h, int w, int h8, int w8, int s,
+                              int up_mode, int cpad, void* stream) {
+  return warp_launch(hr_prev, lr_flow, lr_curr, out, n, c, h, w, h8, w8, s, up_mode, cpad, true,
+                     stream);
+}
+
+int tg_maxpool2x2_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "maxpool2x2: null pointer");
+  TG_REQUIRE(n > 0 && h >= 2 && w >= 2 && c > 0 && c % 8 == 0, TG_E_INVALID,
+             "maxpool2x2: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)y, n, h, w, c / 8);
+  TG_CUDA_LAUNCH_CHECK("maxpool2x2");
+  return TG_OK;
+}
+
+int tg_upsample2x_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w, int c,
+                                    void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "upsample2x: null pointer");
+  TG_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, TG_E_INVALID, "upsample2x: bad shape");
+  const size_t total = (size_t)n * (2 * h) * (2 * w) * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)y, n, h, w, c / 8);
+  TG_CUDA_LAUNCH_CHECK("upsample2x");
+  return TG_OK;
+}
+
+int tg_pack_pair_nhwc_f16(const float* x1, const float* x2, void* y, int n, int c, int h, int w,
+                          int cpad, void* stream) {
+  TG_REQUIRE(x1 && x2 && y, TG_E_INVALID, "pack_pair: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && cpad % 8 == 0 && 2 * c <= cpad, TG_E_INVALID,
+             "pack_pair: bad shape");
+  const size_t total = (size_t)n * h * w * (cpad / 8);
+  pack_pair_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x1, x2, (uint4*)y, n, c, h, w, cpad / 8, 0, 1);
+  TG_CUDA_LAUNCH_CHECK("pack_pair");
+  return TG_OK;
+}
+
+int tg_nchw_f32_to_nhwc_f16(const float* x, void* y, int n, int c, int h, int w, int cpad,
+                            int c_offset, void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "nchw_to_nhwc: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && cpad % 8 == 0 && c_offset >= 0 &&
+                 c_offset + c <= cpad, TG_E_INVALID, "nchw_to_nhwc: bad shape");
+  // c_offset == 0: writes every channel vector (zero padded); c_offset > 0: only the vectors it
+  // touches, which must not be shared with other sources (c_offset % 8 == 0).
+  TG_REQUIRE(c_offset % 8 == 0, TG_E_UNSUPPORTED, "nchw_to_nhwc: c_offset must be a multiple of 8");
+  const size_t total = (size_t)n * h * w * (cpad / 8);
+  pack_pair_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, nullptr, (uint4*)y, n, c, h, w, cpad / 8, c_offset, c_offset == 0 ? 1 : 0);
+  TG_CUDA_LAUNCH_CHECK("nchw_to_nhwc");
+  return TG_OK;
+}
+
+int tg_nhwc_f16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w, int cpad,
+                            void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "nhwc_to_nchw: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && c <= cpad, TG_E_INVALID, "nhwc_to_nchw: bad shape");
+  const size_t total = (size_t)n * c * h * w;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, y, n, c, h, w, cpad);
+  TG_CUDA_LAUNCH_CHECK("nhwc_to_nchw");
+  return TG_OK;
+}
+
+int tg_backward_warp_nchw_f32(const float* x, const float* flow, float* y, int n, int c, int h,
+                              int w, void* stream) {
+  TG_REQUIRE(x && flow && y, TG_E_INVALID, "backward_warp: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "backward_warp: bad shape");
+  const size_t total = (size_t)n * h * w;
+  backward_warp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, flow, y, n, c, h, w);
+  TG_CUDA_LAUNCH_CHECK("backward_warp");
+  return TG_OK;
+}
+
+int tg_space_to_depth_nchw_f32(const float* x, float* y, int n, int c, int h, int w, int s,
+                               void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "space_to_depth: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && s > 0 && h >= s && w >= s, TG_E_INVALID, "space_to_depth: bad shape");
+  const size_t total = (size_t)n * c * s * s * (h / s) * (w / s);
+  space_to_depth_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w, s);
+  TG_CUDA_LAUNCH_CHECK("space_to_depth");
+  return TG_OK;
+}
+
+int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int win, int h, int w,
+                         int s, int up_mode, float mul, void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "upsample: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && hin > 0 && win > 0 && h >= hin && w >= win && s >= 1, TG_E_INVALID,
+             "upsample: bad shape");
+  TG_REQUIRE((h - hin) < hin && (w - win) < win, TG_E_INVALID, "upsample: reflect pad too large");
+  TG_REQUIRE(up_mode == TG_UP_BICUBIC || up_mode == TG_UP_BILINEAR, TG_E_INVALID, "upsample: up_mode");
+  const size_t total = (size_t)n * c * h * s * w * s;
+  upsample_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      x, y, n * c, hin, win, h, w, s, up_mode, mul);
+  TG_CUDA_LAUNCH_CHECK("upsample");
+  return TG_OK;
+}
+
+int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int w, void* stream) {
+  TG_REQUIRE(x && y, TG_E_INVALID, "float_to_uint8: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "float_to_uint8: bad shape");
+  const size_t total = (size_t)n * h * w;
+  to_uint8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
+  TG_CUDA_LAUNCH_CHECK("float_to_uint8");
+  return TG_OK;
+}
+
+}  // extern "C"

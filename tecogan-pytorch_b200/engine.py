@@ -1,0 +1,146 @@
+"""Clip streaming engine: n lock-stepped clips through the FRNet recurrence with static device
+buffers, one CUDA graph per ping-pong parity, pinned host staging and copy streams.
+
+Replaces the per-frame host loop of FRNet.infer_sequence (reference tecogan_nets.py:269-281):
+the reference does an H2D copy, ~60 library launches, a device sync, a D2H copy and a NumPy
+uint8 conversion per frame; here a frame is one graph replay, the uint8/HWC conversion is a
+kernel (tg_float_to_uint8_nhwc) and the copies overlap compute on side streams.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def _use_graph():
+    return os.environ.get('TECOGAN_B200_GRAPH', '1') != '0'
+
+
+class ClipEngine:
+    def __init__(self, net, n, c, h, w, device, use_graph=None):
+        self.net, self.n, self.c, self.h, self.w = net, n, c, h, w
+        self.device = torch.device(device)
+        s = net.scale
+        self.H, self.W = s * h, s * w
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.lr = [torch.zeros(n, c, h, w, device=dev) for _ in range(2)]
+            self.hr = [torch.zeros(n, c, self.H, self.W, device=dev) for _ in range(2)]
+            self.u8 = [torch.empty(n, self.H, self.W, c, dtype=torch.uint8, device=dev) for _ in range(2)]
+            self.use_graph = _use_graph() if use_graph is None else use_graph
+            self.graphs = [None, None]
+            self.main = torch.cuda.Stream(device=dev)
+            self.h2d = torch.cuda.Stream(device=dev)
+            self.d2h = torch.cuda.Stream(device=dev)
+            self.launches_per_step = None
+            if self.use_graph:
+                self._capture()
+
+    # one frame: parity p consumes lr[p] (current), lr[p^1] (previous), hr[p^1] -> hr[p], u8[p]
+    def _enqueue(self, p):
+        self.net.step_into(self.lr[p], self.lr[p ^ 1], self.hr[p ^ 1], self.hr[p])
+        ops.float_to_uint8_nhwc(self.hr[p], self.u8[p])
+
+    def _capture(self):
+        with torch.cuda.device(self.device):
+            warm = torch.cuda.Stream(device=self.device)
+            warm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(warm):
+                for p in (0, 1):            # builds packed weights, sets kernel attributes
+                    self._enqueue(p)
+            torch.cuda.current_stream().wait_stream(warm)
+            torch.cuda.synchronize(self.device)
+            pool = None
+            for p in (0, 1):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    self._enqueue(p)
+                pool = g.pool()
+                self.graphs[p] = g
+            self.reset()
+
+    def reset(self):
+        """lr_prev = hr_prev = 0 (reference tecogan_nets.py:269-270)."""
+        with torch.cuda.device(self.device):
+            for t in self.lr + self.hr:
+                t.zero_()
+
+    def run_frame(self, p):
+        """Enqueue frame with parity p on the current stream."""
+        if self.graphs[p] is not None:
+            self.graphs[p].replay()
+        else:
+            self._enqueue(p)
+
+    def run_clips(self, lr_host, out_host=None):
+        """lr_host: pinned (or pageable) CPU tensor [t,n,c,h,w] fp32 (or a CUDA tensor of that
+        shape); returns pinned uint8 tensor [t,n,H,W,c].  Copies run on side streams and overlap
+        the graph replays; one synchronisation at the end."""
+        t = lr_host.shape[0]
+        if out_host is None:
+            out_host = torch.empty((t, self.n, self.H, self.W, self.c), dtype=torch.uint8).pin_memory()
+        with torch.cuda.device(self.device):
+            self.main.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.main):
+                self.reset()
+            in_ready = [None, None]
+            frame_done = [None, None]      # compute of parity p finished (u8[p] valid, lr[p] consumed)
+            out_copied = [None, None]      # D2H of u8[p] finished
+            self.h2d.wait_stream(self.main)
+            for i in range(t):
+                p = i & 1
+                with torch.cuda.stream(self.h2d):
+                    # lr[p] was last READ by frame i-1 (as lr_prev); wait for that frame
+                    if frame_done[p ^ 1] is not None:
+                        self.h2d.wait_event(frame_done[p ^ 1])
+                    self.lr[p].copy_(lr_host[i], non_blocking=True)
+                    in_ready[p] = torch.cuda.Event()
+                    in_ready[p].record(self.h2d)
+                with torch.cuda.stream(self.main):
+                    self.main.wait_event(in_ready[p])
+                    if out_copied[p] is not None:
+                        self.main.wait_event(out_copied[p])    # u8[p] free to overwrite
+                    self.run_frame(p)
+                    frame_done[p] = torch.cuda.Event()
+                    frame_done[p].record(self.main)
+                with torch.cuda.stream(self.d2h):
+                    self.d2h.wait_event(frame_done[p])
+                    out_host[i].copy_(self.u8[p], non_blocking=True)
+                    out_copied[p] = torch.cuda.Event()
+                    out_copied[p].record(self.d2h)
+            self.d2h.synchronize()
+            self.main.synchronize()
+        return out_host
+
+
+_ENGINES = {}
+
+
+def get_engine(net, n, c, h, w, device):
+    key = (id(net), n, c, h, w, str(device))
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = ClipEngine(net, n, c, h, w, device)
+        _ENGINES[key] = eng
+    else:
+        # parameters may have changed since capture: repack in place (graphs read the same buffers)
+        net.refresh_packed_weights()
+    return eng
+
+
+def infer_clips(net, lr_data, device):
+    """lr_data [n,t,c,h,w] fp32 (CPU or CUDA) -> np.uint8 [n,t,H,W,c]."""
+    if lr_data.dim() != 5:
+        raise ValueError('infer_clips expects ntchw')
+    n, t, c, h, w = lr_data.shape
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise ops.L.TecoganB200Error('tecogan-b200 runs on CUDA devices only (no CPU path)')
+    eng = get_engine(net, n, c, h, w, device)
+    src = lr_data.detach().float().transpose(0, 1).contiguous()      # t,n,c,h,w
+    if not src.is_cuda and not src.is_pinned():
+        src = src.pin_memory()
+    out = eng.run_clips(src)
+    return out.numpy().transpose(1, 0, 2, 3, 4)

@@ -1,0 +1,70 @@
+"""Drop-in for the functional ops of codes/utils/net_utils.py (reference lines 36-156):
+space_to_depth, backward_warp, get_upsampling_func, BicubicUpsampler -- same names, argument
+meaning and error behaviour, executed by libtecogan_b200 on NCHW fp32 CUDA tensors.
+"""
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from . import ops
+
+
+def _f32(t, name):
+    if not t.is_cuda:
+        raise L.TecoganB200Error(f'{name} must be a CUDA tensor: tecogan-b200 has no CPU path')
+    return t.detach().float().contiguous()
+
+
+def space_to_depth(x, scale):
+    """Equivalent to tf.space_to_depth(): out[n,(sy*s+sx)*C+c,oh,ow] = x[n,c,oh*s+sy,ow*s+sx]."""
+    return ops.space_to_depth(_f32(x, 'x'), scale)
+
+
+def backward_warp(x, flow, mode='bilinear', padding_mode='border'):
+    """Backward warp `x` (nchw) according to `flow` (n2hw): bilinear, border clamp,
+    align_corners=True -- the only combination the reference ever uses."""
+    if mode != 'bilinear' or padding_mode != 'border':
+        raise ValueError(f'Unsupported warp mode: {mode}/{padding_mode}')
+    return ops.backward_warp(_f32(x, 'x'), _f32(flow, 'flow'))
+
+
+class BicubicUpsampler(nn.Module):
+    """TF-style bicubic (a=-0.75, no half-pixel shift, replicate border); keeps the reference's
+    `kernels` buffer [scale,4] so BD checkpoints load strictly."""
+
+    def __init__(self, scale_factor, a=-0.75):
+        super().__init__()
+        cubic = torch.tensor([[0, a, -2 * a, a], [1, 0, -(a + 3), a + 2],
+                              [0, -a, (2 * a + 3), -(a + 2)], [0, 0, a, -a]], dtype=torch.float32)
+        ks = [cubic @ torch.tensor([1.0, t, t * t, t * t * t]) for t in
+              (1.0 * d / scale_factor for d in range(scale_factor))]
+        self.scale_factor = scale_factor
+        self.register_buffer('kernels', torch.stack(ks))
+        if a != -0.75:
+            raise ValueError('tecogan-b200 BicubicUpsampler is built for a=-0.75')
+
+    def forward(self, input):
+        return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BICUBIC)
+
+
+class BilinearUpsampler:
+    """F.interpolate(scale_factor=s, mode='bilinear', align_corners=False) for BI degradation.
+    A plain callable (not a Module), like the reference's functools.partial: no state_dict keys."""
+
+    def __init__(self, scale_factor):
+        self.scale_factor = scale_factor
+
+    def __call__(self, input):
+        return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BILINEAR)
+
+
+def get_upsampling_func(scale=4, degradation='BI'):
+    if degradation == 'BI':
+        return BilinearUpsampler(scale)
+    if degradation == 'BD':
+        return BicubicUpsampler(scale_factor=scale)
+    raise ValueError(f'Unrecognized degradation type: {degradation}')
+
+
+def up_mode_of(upsample_func):
+    return L.UP_BICUBIC if isinstance(upsample_func, BicubicUpsampler) else L.UP_BILINEAR

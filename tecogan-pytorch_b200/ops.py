@@ -1,0 +1,273 @@
+"""Torch-tensor front end of the C ABI (include/tecogan_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the CUDA stream; every operation below is
+one call into libtecogan_b200.so on ``torch.cuda.current_stream()``.  No op has a torch/CPU
+fallback -- a tensor that is not on a CUDA device is an error.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import lib as L
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _req(t, dtype, name, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise L.TecoganB200Error(f'{name}: expected a CUDA tensor (no CPU fallback exists)')
+    if t.dtype != dtype:
+        raise L.TecoganB200Error(f'{name}: expected dtype {dtype}, got {t.dtype}')
+    if ndim is not None and t.dim() != ndim:
+        raise L.TecoganB200Error(f'{name}: expected {ndim} dims, got {tuple(t.shape)}')
+    if not t.is_contiguous():
+        raise L.TecoganB200Error(f'{name}: tensor must be contiguous')
+    return t
+
+
+def sm_count():
+    out = ctypes.c_int(0)
+    L.check(L.load().tg_device_sm_count(ctypes.byref(out)), 'tg_device_sm_count')
+    return out.value
+
+
+def pad64(c):
+    return (c + 63) // 64 * 64
+
+
+# ---------------------------------------------------------------------------- conv layers
+class PackedConv:
+    """One 3x3 conv / stride-2 transposed conv of the path with device-packed fp16 weights.
+
+    weight: nn.Conv2d layout [cout,cin,3,3] or nn.ConvTranspose2d layout [cin,cout,3,3] (fp32).
+    Stored channel counts are padded to multiples of 64 (cin) and to 64/128/256 or 16 (cout).
+    """
+
+    def __init__(self, weight, bias, kind=L.CONV_3X3, act=L.ACT_NONE, epilogue=L.EPI_NHWC_F16):
+        self.kind, self.act, self.epilogue = kind, act, epilogue
+        if kind == L.CONV_3X3:
+            self.cout_real, self.cin_real = weight.shape[0], weight.shape[1]
+        else:
+            self.cin_real, self.cout_real = weight.shape[0], weight.shape[1]
+        self.cin = pad64(self.cin_real)
+        self.cout = pad64(self.cout_real) if epilogue == L.EPI_NHWC_F16 else 16
+        self.packed = None
+        self.bias = None
+        self._ver = None
+        self.refresh(weight, bias)
+
+    def refresh(self, weight, bias):
+        """(Re)pack when the parameters changed (optimizer step / load_state_dict)."""
+        ver = (weight._version, bias._version, weight.data_ptr(), bias.data_ptr())
+        if ver == self._ver:
+            return
+        lib = L.load()
+        w = _req(weight.detach(), torch.float32, 'weight', 4)
+        nbytes = lib.tg_packed_weight_bytes(self.cin, self.cout)
+        if self.packed is None:
+            self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+            self.bias = torch.zeros(self.cout, dtype=torch.float32, device=w.device)
+        if self.kind == L.CONV_3X3:
+            rc = lib.tg_pack_conv3x3_weights(_ptr(w), self.cout_real, self.cin_real, _ptr(self.packed),
+                                             self.cout, self.cin, _stream())
+        else:
+            rc = lib.tg_pack_convT3x3s2_weights(_ptr(w), self.cin_real, self.cout_real,
+                                                _ptr(self.packed), self.cout, self.cin, _stream())
+        L.check(rc, 'tg_pack_weights')
+        self.bias[:self.cout_real].copy_(bias.detach())
+        self._ver = ver
+
+    def out_shape(self, n, h, w):
+        if self.epilogue == L.EPI_NHWC_F16:
+            if self.kind == L.CONVT_3X3_S2:
+                return (n, 2 * h, 2 * w, self.cout), torch.float16
+            return (n, h, w, self.cout), torch.float16
+        return (n, self.cout_real, h, w), torch.float32
+
+    def __call__(self, x, y=None, residual=None, aux=None, up_scale=0, up_mode=0, impl=None,
+                 a_mode=None, max_ctas=0):
+        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None)."""
+        _req(x, torch.float16, 'conv input', 4)
+        n, h, w, cin = x.shape
+        if cin != self.cin:
+            raise L.TecoganB200Error(f'conv input has {cin} channels, layer expects {self.cin}')
+        shape, dtype = self.out_shape(n, h, w)
+        if y is None:
+            y = torch.empty(shape, dtype=dtype, device=x.device)
+        else:
+            _req(y, dtype, 'conv output')
+            if tuple(y.shape) != shape:
+                raise L.TecoganB200Error(f'conv output shape {tuple(y.shape)} != {shape}')
+        if residual is not None:
+            _req(residual, torch.float16, 'residual', 4)
+            if tuple(residual.shape) != (n, h, w, self.cout):
+                raise L.TecoganB200Error('residual shape mismatch')
+        if aux is not None:
+            _req(aux, torch.float32, 'aux', 4)
+        d = L.ConvDesc()
+        d.x, d.weights, d.bias = x.data_ptr(), self.packed.data_ptr(), self.bias.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.y = y.data_ptr()
+        d.aux = aux.data_ptr() if aux is not None else None
+        d.n, d.h, d.w, d.cin, d.cout, d.cout_real = n, h, w, self.cin, self.cout, self.cout_real
+        d.kind, d.act, d.epilogue = self.kind, self.act, self.epilogue
+        d.up_scale, d.up_mode = up_scale, up_mode
+        d.a_mode = default_a_mode() if a_mode is None else a_mode
+        d.max_ctas = max_ctas
+        impl = impl or default_conv_impl()
+        lib = L.load()
+        if impl == 'tcgen05':
+            L.check(lib.tg_conv_tcgen05(ctypes.byref(d), _stream()), 'tg_conv_tcgen05')
+        elif impl == 'simt':
+            L.check(lib.tg_conv_simt(ctypes.byref(d), _stream()), 'tg_conv_simt')
+        else:
+            raise L.TecoganB200Error(f'unknown conv impl {impl!r}')
+        return y
+
+
+def default_conv_impl():
+    """'tcgen05' (the product path) unless TECOGAN_B200_CONV=simt selects the CUDA-core
+    cross-check kernel (bring-up / debugging only)."""
+    return os.environ.get('TECOGAN_B200_CONV', 'tcgen05')
+
+
+def default_a_mode():
+    return {'auto': L.AMODE_AUTO, 'halo': L.AMODE_HALO, 'tap': L.AMODE_TAP}[
+        os.environ.get('TECOGAN_B200_AMODE', 'auto')]
+
+
+# ---------------------------------------------------------------------------- fused warp
+def warp_s2d_concat_hrflow(hr_prev, hr_flow, lr_curr, scale, out=None, cpad=64):
+    _req(hr_prev, torch.float32, 'hr_prev', 4)
+    _req(hr_flow, torch.float32, 'hr_flow', 4)
+    _req(lr_curr, torch.float32, 'lr_curr', 4)
+    n, c, h, w = lr_curr.shape
+    if tuple(hr_prev.shape) != (n, c, scale * h, scale * w) or tuple(hr_flow.shape) != (n, 2, scale * h, scale * w):
+        raise L.TecoganB200Error('warp_s2d_concat: shape mismatch')
+    if out is None:
+        out = torch.empty((n, h, w, cpad), dtype=torch.float16, device=lr_curr.device)
+    L.check(L.load().tg_warp_s2d_concat_hrflow(_ptr(hr_prev), _ptr(hr_flow), _ptr(lr_curr), _ptr(out),
+                                               n, c, h, w, scale, cpad, _stream()),
+            'tg_warp_s2d_concat_hrflow')
+    return out
+
+
+def warp_s2d_concat_lrflow(hr_prev, lr_flow, lr_curr, scale, up_mode, out=None, cpad=64):
+    _req(hr_prev, torch.float32, 'hr_prev', 4)
+    _req(lr_flow, torch.float32, 'lr_flow', 4)
+    _req(lr_curr, torch.float32, 'lr_curr', 4)
+    n, c, h, w = lr_curr.shape
+    h8, w8 = lr_flow.shape[2], lr_flow.shape[3]
+    if tuple(hr_prev.shape) != (n, c, scale * h, scale * w) or lr_flow.shape[0] != n or lr_flow.shape[1] != 2:
+        raise L.TecoganB200Error('warp_s2d_concat: shape mismatch')
+    if out is None:
+        out = torch.empty((n, h, w, cpad), dtype=torch.float16, device=lr_curr.device)
+    L.check(L.load().tg_warp_s2d_concat_lrflow(_ptr(hr_prev), _ptr(lr_flow), _ptr(lr_curr), _ptr(out),
+                                               n, c, h, w, h8, w8, scale, up_mode, cpad, _stream()),
+            'tg_warp_s2d_concat_lrflow')
+    return out
+
+
+# ---------------------------------------------------------------------------- NHWC fp16 helpers
+def maxpool2x2(x, y=None):
+    _req(x, torch.float16, 'maxpool input', 4)
+    n, h, w, c = x.shape
+    if y is None:
+        y = torch.empty((n, h // 2, w // 2, c), dtype=torch.float16, device=x.device)
+    L.check(L.load().tg_maxpool2x2_nhwc_f16(_ptr(x), _ptr(y), n, h, w, c, _stream()), 'tg_maxpool2x2')
+    return y
+
+
+def upsample2x(x, y=None):
+    _req(x, torch.float16, 'upsample2x input', 4)
+    n, h, w, c = x.shape
+    if y is None:
+        y = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.float16, device=x.device)
+    L.check(L.load().tg_upsample2x_bilinear_nhwc_f16(_ptr(x), _ptr(y), n, h, w, c, _stream()),
+            'tg_upsample2x')
+    return y
+
+
+def pack_pair(x1, x2, y=None, cpad=64):
+    _req(x1, torch.float32, 'x1', 4)
+    _req(x2, torch.float32, 'x2', 4)
+    n, c, h, w = x1.shape
+    if y is None:
+        y = torch.empty((n, h, w, cpad), dtype=torch.float16, device=x1.device)
+    L.check(L.load().tg_pack_pair_nhwc_f16(_ptr(x1), _ptr(x2), _ptr(y), n, c, h, w, cpad, _stream()),
+            'tg_pack_pair')
+    return y
+
+
+def nchw_to_nhwc(x, cpad=None, y=None):
+    _req(x, torch.float32, 'x', 4)
+    n, c, h, w = x.shape
+    cpad = cpad or pad64(c)
+    if y is None:
+        y = torch.empty((n, h, w, cpad), dtype=torch.float16, device=x.device)
+    L.check(L.load().tg_nchw_f32_to_nhwc_f16(_ptr(x), _ptr(y), n, c, h, w, cpad, 0, _stream()),
+            'tg_nchw_to_nhwc')
+    return y
+
+
+def nhwc_to_nchw(x, c, y=None):
+    _req(x, torch.float16, 'x', 4)
+    n, h, w, cpad = x.shape
+    if y is None:
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.load().tg_nhwc_f16_to_nchw_f32(_ptr(x), _ptr(y), n, c, h, w, cpad, _stream()),
+            'tg_nhwc_to_nchw')
+    return y
+
+
+# ---------------------------------------------------------------------------- NCHW fp32 module ops
+def backward_warp(x, flow, y=None):
+    _req(x, torch.float32, 'x', 4)
+    _req(flow, torch.float32, 'flow', 4)
+    n, c, h, w = x.shape
+    if tuple(flow.shape) != (n, 2, h, w):
+        raise L.TecoganB200Error('backward_warp: flow shape mismatch')
+    if y is None:
+        y = torch.empty_like(x)
+    L.check(L.load().tg_backward_warp_nchw_f32(_ptr(x), _ptr(flow), _ptr(y), n, c, h, w, _stream()),
+            'tg_backward_warp')
+    return y
+
+
+def space_to_depth(x, scale, y=None):
+    _req(x, torch.float32, 'x', 4)
+    n, c, h, w = x.shape
+    if y is None:
+        y = torch.empty((n, c * scale * scale, h // scale, w // scale), dtype=torch.float32, device=x.device)
+    L.check(L.load().tg_space_to_depth_nchw_f32(_ptr(x), _ptr(y), n, c, h, w, scale, _stream()),
+            'tg_space_to_depth')
+    return y
+
+
+def upsample(x, scale, up_mode, out_hw=None, mul=1.0, y=None):
+    """mul * upsample_func(reflect_pad(x -> out_hw)); out_hw defaults to x's own size."""
+    _req(x, torch.float32, 'x', 4)
+    n, c, hin, win = x.shape
+    h, w = out_hw if out_hw is not None else (hin, win)
+    if y is None:
+        y = torch.empty((n, c, h * scale, w * scale), dtype=torch.float32, device=x.device)
+    L.check(L.load().tg_upsample_nchw_f32(_ptr(x), _ptr(y), n, c, hin, win, h, w, scale, up_mode,
+                                          ctypes.c_float(mul), _stream()), 'tg_upsample')
+    return y
+
+
+def float_to_uint8_nhwc(x, y=None):
+    _req(x, torch.float32, 'x', 4)
+    n, c, h, w = x.shape
+    if y is None:
+        y = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    L.check(L.load().tg_float_to_uint8_nhwc(_ptr(x), _ptr(y), n, c, h, w, _stream()),
+            'tg_float_to_uint8')
+    return y

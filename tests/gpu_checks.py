@@ -1,0 +1,403 @@
+"""GPU parity checks of the CUDA path against the CPU oracle (oracle/) and the committed golden
+fixtures (tests/golden).  Each check is a plain function returning a dict of measured errors and
+raising AssertionError on a parity failure, so the same code backs
+
+  * tests/test_gpu_parity.py   (pytest -m gpu, what the driver runs), and
+  * tests/gpu_diag.py          (each check in its own process with a timeout; bring-up tool).
+
+Nothing here reads /root/reference.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import tecogan_b200 as T                      # noqa: E402
+from oracle import ops_oracle as K            # noqa: E402
+from oracle import frnet_oracle as O          # noqa: E402
+
+ops = sys.modules['tecogan-pytorch_b200.ops']
+L = sys.modules['tecogan-pytorch_b200.lib']
+G = os.path.join(ROOT, 'tests', 'golden')
+DEV = 'cuda:0'
+
+
+def rand(seed, *shape, lo=0.0, hi=1.0):
+    return torch.from_numpy(np.random.default_rng(seed).uniform(lo, hi, size=shape).astype(np.float32))
+
+
+def relmax(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def rell2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+def f16(x):
+    """round to fp16 and back (the storage precision of the CUDA path)"""
+    return x.half().float()
+
+
+def nhwc(x_nchw_f32, cpad=64):
+    """CPU NCHW fp32 -> CUDA NHWC fp16 padded to cpad channels"""
+    n, c, h, w = x_nchw_f32.shape
+    y = torch.zeros(n, h, w, cpad, dtype=torch.float16)
+    y[..., :c] = x_nchw_f32.permute(0, 2, 3, 1).half()
+    return y.to(DEV)
+
+
+def from_nhwc(y, c):
+    return y[..., :c].float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+# =============================================================================== elementwise
+def check_warp_hrflow(scale=4, h=11, w=37, n=2):
+    hr_prev = rand(1, n, 3, scale * h, scale * w)
+    flow = rand(2, n, 2, scale * h, scale * w, lo=-6, hi=6)
+    flow[0, :, 0, 0] = torch.tensor([-100.0, 100.0])
+    flow[0, :, -1, -1] = torch.tensor([100.0, -100.0])
+    lr = rand(3, n, 3, h, w)
+    got = ops.warp_s2d_concat_hrflow(hr_prev.to(DEV), flow.to(DEV), lr.to(DEV), scale)
+    torch.cuda.synchronize()
+    ref = K.warp_s2d_concat(hr_prev.numpy(), flow.numpy(), lr.numpy(), scale)
+    c_used = (scale * scale + 1) * 3
+    got_f = from_nhwc(got, c_used).numpy()
+    # index math: every output element must be the fp16 rounding of the oracle value up to the
+    # closed-form grid (x+u vs the reference's normalised round trip: <= ~1e-4 px)
+    err = np.abs(got_f - ref).max()
+    assert err <= 2e-3, f'warp_hrflow max abs err {err}'
+    assert np.array_equal(got_f[:, :3], f16(lr).numpy()), 'lr_curr channels must be exact fp16 copies'
+    assert float(got[..., c_used:].abs().max()) == 0.0, 'pad channels must be zero'
+    # space_to_depth placement exactness: integer flow -> warp is an exact gather
+    flow_i = torch.round(flow)
+    got_i = ops.warp_s2d_concat_hrflow(hr_prev.to(DEV), flow_i.to(DEV), lr.to(DEV), scale)
+    ref_i = K.warp_s2d_concat(hr_prev.numpy(), flow_i.numpy(), lr.numpy(), scale, exact_reference_grid=False)
+    assert np.array_equal(from_nhwc(got_i, c_used).numpy(), f16(torch.from_numpy(ref_i)).numpy()), \
+        'integer-flow warp + space_to_depth must be bit exact'
+    return {'max_abs': float(err)}
+
+
+def check_warp_lrflow(scale=4, mode='BD', h=18, w=28, n=2):
+    h8, w8 = h // 8 * 8, w // 8 * 8
+    hr_prev = rand(4, n, 3, scale * h, scale * w)
+    lr_flow = rand(5, n, 2, h8, w8, lo=-3, hi=3)
+    lr = rand(6, n, 3, h, w)
+    up_mode = L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR
+    got = ops.warp_s2d_concat_lrflow(hr_prev.to(DEV), lr_flow.to(DEV), lr.to(DEV), scale, up_mode)
+    pad = K.reflect_pad_flow(lr_flow.numpy(), h - h8, w - w8)
+    up = K.bicubic_upsample(pad, scale) if mode == 'BD' else K.bilinear_upsample(pad, scale)
+    hr_flow = np.float32(scale) * up
+    ref = K.warp_s2d_concat(hr_prev.numpy(), hr_flow, lr.numpy(), scale)
+    c_used = (scale * scale + 1) * 3
+    err = np.abs(from_nhwc(got, c_used).numpy() - ref).max()
+    assert err <= 2e-3, f'warp_lrflow({mode},{scale}) max abs err {err}'
+    # the standalone flow upsampler must agree with the oracle to fp32 rounding
+    hf = ops.upsample(lr_flow.to(DEV), scale, up_mode, out_hw=(h, w), mul=float(scale)).cpu().numpy()
+    e2 = np.abs(hf - hr_flow).max()
+    assert e2 <= 2e-5, f'flow upsample err {e2}'
+    return {'max_abs': float(err), 'flow_up_abs': float(e2)}
+
+
+def check_pool_upsample():
+    x = rand(7, 2, 64, 13, 22, lo=-2, hi=2)
+    xg = nhwc(x)
+    p = from_nhwc(ops.maxpool2x2(xg), 64).numpy()
+    assert np.array_equal(p, K.maxpool2x2(f16(x).numpy())), 'maxpool must be exact'
+    u = from_nhwc(ops.upsample2x(xg), 64).numpy()
+    ref = K.bilinear_upsample(f16(x).numpy(), 2)
+    err = np.abs(u - ref).max()
+    assert err <= 2e-3, f'upsample2x err {err}'
+    a, b = rand(8, 2, 3, 9, 14), rand(9, 2, 3, 9, 14)
+    pk = ops.pack_pair(a.to(DEV), b.to(DEV))
+    assert np.array_equal(from_nhwc(pk, 6).numpy(), f16(torch.cat([a, b], 1)).numpy())
+    assert float(pk[..., 6:].abs().max()) == 0.0
+    return {'upsample2x_abs': float(err)}
+
+
+def check_module_ops():
+    g = np.load(os.path.join(G, 'ops.npz'))
+    x = rand(20, 2, 3, 20, 24)
+    flow = rand(21, 2, 2, 20, 24, lo=-4.0, hi=4.0)
+    flow[0, :, 0, 0] = torch.tensor([-30.0, 40.0])
+    w = T.backward_warp(x.to(DEV), flow.to(DEV)).cpu().numpy()
+    e_w = np.abs(w - g['warped']).max()
+    assert e_w <= 2e-5, f'backward_warp vs reference golden {e_w}'
+    s4 = T.space_to_depth(rand(22, 2, 3, 16, 24).to(DEV), 4).cpu().numpy()
+    s2 = T.space_to_depth(rand(22, 2, 3, 16, 24).to(DEV), 2).cpu().numpy()
+    assert np.array_equal(s4, g['s2d4']) and np.array_equal(s2, g['s2d2']), 'space_to_depth bit exact'
+    xs = rand(23, 1, 3, 9, 11).to(DEV)
+    e_b = max(np.abs(T.get_upsampling_func(4, 'BD')(xs).cpu().numpy() - g['bic4']).max(),
+              np.abs(T.get_upsampling_func(2, 'BD')(xs).cpu().numpy() - g['bic2']).max(),
+              np.abs(T.get_upsampling_func(4, 'BI')(xs).cpu().numpy() - g['bil4']).max(),
+              np.abs(T.get_upsampling_func(2, 'BI')(xs).cpu().numpy() - g['bil2']).max())
+    assert e_b <= 2e-6, f'upsample_func vs reference golden {e_b}'
+    q_in = torch.from_numpy(g['q_in']).reshape(1, 1, 1, -1).to(DEV)
+    q = ops.float_to_uint8_nhwc(q_in).cpu().numpy().reshape(-1)
+    assert np.array_equal(q, g['q']), 'uint8 quantisation (round-half-even) must be bit exact'
+    return {'warp_abs': float(e_w), 'upsample_abs': float(e_b)}
+
+
+# =============================================================================== convolutions
+def _conv_ref(x, wt, b, kind, act, residual=None):
+    """CPU fp32 reference on fp16-rounded operands."""
+    xr, wr = f16(x), f16(wt)
+    if kind == L.CONV_3X3:
+        y = F.conv2d(xr, wr, b, padding=1)
+    else:
+        y = torch.from_numpy(K.conv_transpose3x3s2_parity(xr.numpy(), wr.numpy(), b.numpy()))
+    if act == L.ACT_RELU:
+        y = y.clamp_min(0)
+    elif act == L.ACT_LRELU02:
+        y = torch.where(y >= 0, y, 0.2 * y)
+    if residual is not None:
+        y = y + f16(residual)
+    return y
+
+
+def check_conv(impl='tcgen05', a_mode=None, cin=64, cout=64, h=20, w=24, n=2, kind=None,
+               act=None, residual=False, seed=30, cin_real=None, cout_real=None):
+    kind = L.CONV_3X3 if kind is None else kind
+    act = L.ACT_RELU if act is None else act
+    cin_real = cin_real or cin
+    cout_real = cout_real or cout
+    x = rand(seed, n, cin_real, h, w, lo=-1, hi=1)
+    bound = 1.5 / np.sqrt(9 * cin_real)
+    wshape = (cout_real, cin_real, 3, 3) if kind == L.CONV_3X3 else (cin_real, cout_real, 3, 3)
+    wt = rand(seed + 1, *wshape, lo=-bound, hi=bound)
+    b = rand(seed + 2, cout_real, lo=-0.5, hi=0.5)
+    res = rand(seed + 3, n, cout_real, h, w, lo=-1, hi=1) if residual else None
+    pc = ops.PackedConv(wt.to(DEV), b.to(DEV), kind, act)
+    assert pc.cin == cin and pc.cout == cout
+    y = pc(nhwc(x, cin), residual=nhwc(res, cout) if residual else None, impl=impl, a_mode=a_mode)
+    torch.cuda.synchronize()
+    ref = _conv_ref(x, wt, b, kind, act, res)
+    got = from_nhwc(y, cout_real)
+    e = relmax(got.numpy(), ref.numpy())
+    assert e <= 3e-3, f'conv {impl} amode={a_mode} cin={cin} cout={cout} kind={kind}: rel max err {e}'
+    if cout_real < cout:
+        assert float(y[..., cout_real:].abs().max()) == 0.0, 'padded output channels must be zero'
+    return {'rel_max': e, 'rel_l2': rell2(got.numpy(), ref.numpy())}
+
+
+def check_conv_vs_simt(a_mode=None, cin=64, cout=64, h=134, w=320, n=1, kind=None, residual=True,
+                       max_ctas=0):
+    """tcgen05 vs the CUDA-core kernel on identical packed weights: only the fp32 summation
+    order differs, so after fp16 rounding they agree to 1 ulp almost everywhere."""
+    kind = L.CONV_3X3 if kind is None else kind
+    residual = residual and kind == L.CONV_3X3
+    x = nhwc(rand(40, n, cin, h, w, lo=-1, hi=1), cin)
+    bound = 1.5 / np.sqrt(9 * cin)
+    wshape = (cout, cin, 3, 3) if kind == L.CONV_3X3 else (cin, cout, 3, 3)
+    pc = ops.PackedConv(rand(41, *wshape, lo=-bound, hi=bound).to(DEV),
+                        rand(42, cout, lo=-0.5, hi=0.5).to(DEV), kind, L.ACT_RELU)
+    res = nhwc(rand(43, n, cout, h, w, lo=-1, hi=1), cout) if residual else None
+    a = pc(x, residual=res, impl='tcgen05', a_mode=a_mode, max_ctas=max_ctas)
+    b = pc(x, residual=res, impl='simt')
+    torch.cuda.synchronize()
+    d = (a.float() - b.float()).abs()
+    e = float(d.max() / b.float().abs().max())
+    frac = float((d > 0).float().mean())
+    assert e <= 2e-3, f'tcgen05 vs simt: rel max {e} (differing elements {frac:.4f})'
+    return {'rel_max': e, 'frac_diff': frac}
+
+
+def check_conv_epilogues(impl='tcgen05'):
+    out = {}
+    # flow head: 24*tanh(conv) -> NCHW fp32 [n,2,h,w]
+    x = rand(50, 2, 64, 16, 24, lo=-1, hi=1)
+    wt = rand(51, 2, 64, 3, 3, lo=-0.08, hi=0.08)
+    b = rand(52, 2, lo=-0.1, hi=0.1)
+    pc = ops.PackedConv(wt.to(DEV), b.to(DEV), L.CONV_3X3, L.ACT_NONE, L.EPI_FLOW_NCHW_F32)
+    y = pc(nhwc(x), impl=impl).cpu()
+    ref = 24 * torch.tanh(F.conv2d(f16(x), f16(wt), b, padding=1))
+    out['flow_rel'] = relmax(y.numpy(), ref.numpy())
+    assert out['flow_rel'] <= 1e-3, out
+    # output head: conv + bias + upsample_func(lr_curr) -> NCHW fp32
+    for mode, s in (('BD', 4), ('BI', 2)):
+        hh, ww = 6 * s, 10 * s
+        x = rand(53, 1, 64, hh, ww, lo=-1, hi=1)
+        wt = rand(54, 3, 64, 3, 3, lo=-0.08, hi=0.08)
+        b = rand(55, 3, lo=-0.1, hi=0.1)
+        lr = rand(56, 1, 3, 6, 10)
+        pc = ops.PackedConv(wt.to(DEV), b.to(DEV), L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
+        y = pc(nhwc(x), aux=lr.to(DEV), up_scale=s, impl=impl,
+               up_mode=L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR).cpu()
+        up = K.bicubic_upsample(lr.numpy(), s) if mode == 'BD' else K.bilinear_upsample(lr.numpy(), s)
+        ref = F.conv2d(f16(x), f16(wt), b, padding=1) + torch.from_numpy(up)
+        out[f'out_{mode}{s}_rel'] = relmax(y.numpy(), ref.numpy())
+        assert out[f'out_{mode}{s}_rel'] <= 1e-3, out
+    return out
+
+
+# =============================================================================== FRNet end to end
+def _net(seed, scale, degradation, gain, nb=10):
+    net = T.FRNet(3, 3, 64, nb, degradation, scale)
+    p = O.make_frnet_params(seed, nb=nb, scale=scale, degradation=degradation, gain=gain)
+    net.load_state_dict(p, strict=True)
+    return net.to(DEV).eval(), p
+
+
+def check_step_golden(tag='g2'):
+    gain = {'g1': 1.0, 'g2': 2.0}[tag]
+    g = np.load(os.path.join(G, f'step_bd4_18x28_{tag}.npz'))
+    net, p = _net(11, 4, 'BD', gain)
+    lr_curr, lr_prev, hr_prev = rand(1, 1, 3, 18, 28), rand(2, 1, 3, 18, 28), rand(3, 1, 3, 72, 112)
+    flow = net.fnet(lr_curr.to(DEV), lr_prev.to(DEV)).cpu().numpy()
+    hr = net.step(lr_curr.to(DEV), lr_prev.to(DEV), hr_prev.to(DEV)).cpu().numpy()
+    out = {'flow_abs': float(np.abs(flow - g['lr_flow']).max()),
+           'flow_absmax_ref': float(np.abs(g['lr_flow']).max()),
+           'hr_rel_l2': rell2(hr, g['hr_curr']), 'hr_rel_max': relmax(hr, g['hr_curr'])}
+    # tolerance stated by north_star: 1e-3 relative for the fp16 path (rel-L2 against the fp32
+    # reference); max-abs is reported and bounded loosely (a white-noise hr_prev amplifies the
+    # fp16 flow error through the warp gradient)
+    assert out['hr_rel_l2'] <= 1e-3, out
+    assert out['hr_rel_max'] <= 1e-2, out
+    assert out['flow_abs'] <= 5e-3 * max(1.0, out['flow_absmax_ref']), out
+    return out
+
+
+def check_step_bi2():
+    g = np.load(os.path.join(G, 'step_bi2_20x24_g2.npz'))
+    net, p = _net(12, 2, 'BI', 2.0)
+    hr = net.step(rand(4, 1, 3, 20, 24).to(DEV), rand(5, 1, 3, 20, 24).to(DEV),
+                  rand(6, 1, 3, 40, 48).to(DEV)).cpu().numpy()
+    out = {'hr_rel_l2': rell2(hr, g['hr_curr']), 'hr_rel_max': relmax(hr, g['hr_curr'])}
+    assert out['hr_rel_l2'] <= 1e-3 and out['hr_rel_max'] <= 1e-2, out
+    return out
+
+
+def check_infer_sequence_golden():
+    g = np.load(os.path.join(G, 'infer_seq_bd4_16x24_g2.npz'))
+    net, p = _net(13, 4, 'BD', 2.0)
+    clip = O.make_clip(7, 4, 3, 16, 24)
+    seq = net.infer_sequence(clip, torch.device(DEV))
+    assert seq.shape == g['hr_seq'].shape and seq.dtype == np.uint8
+    d = np.abs(seq.astype(np.int32) - g['hr_seq'].astype(np.int32))
+    out = {'max_lsb': int(d.max()), 'frac_diff': float((d != 0).mean())}
+    # fp16 path vs fp32 reference after 8-bit quantisation: at most 1 LSB
+    assert out['max_lsb'] <= 1, out
+    # eval-mode forward dispatch (reference FRNet.forward -> infer_sequence)
+    seq2 = net(clip, torch.device(DEV))
+    assert np.array_equal(seq, seq2), 'infer_sequence must be deterministic'
+    return out
+
+
+def check_forward_sequence_golden():
+    g = np.load(os.path.join(G, 'fwd_seq_bd4_16x16_g2.npz'))
+    net, p = _net(14, 4, 'BD', 2.0)
+    net.train()
+    with torch.no_grad():
+        d = net(rand(8, 1, 3, 3, 16, 16).to(DEV))
+    out = {}
+    for k in ('hr_data', 'hr_flow', 'lr_prev', 'lr_curr', 'lr_flow'):
+        assert tuple(d[k].shape) == g[k].shape, k
+        out[k] = rell2(d[k].cpu().numpy(), g[k])
+    assert out['hr_data'] <= 1e-3 and out['lr_flow'] <= 5e-3 and out['hr_flow'] <= 5e-3, out
+    assert out['lr_prev'] == 0.0 and out['lr_curr'] == 0.0
+    try:
+        net(rand(8, 1, 3, 3, 16, 16).to(DEV))
+        raise AssertionError('forward_sequence with autograd enabled must raise')
+    except NotImplementedError:
+        pass
+    return out
+
+
+def check_step_vs_oracle_fullsize(n=1, h=134, w=320, gain=2.0, frames=3):
+    """BASELINE size: recurrence of `frames` steps from zero state on a moving clip, compared
+    with the CPU oracle (fp32) per frame; reports drift and PSNR delta on the uint8 output."""
+    net, p = _net(5, 4, 'BD', gain)
+    clip = O.make_clip(9, frames, 3, h, w)
+    lr_prev = torch.zeros(1, 3, h, w)
+    hr_prev = torch.zeros(1, 3, 4 * h, 4 * w)
+    g_lr_prev, g_hr_prev = lr_prev.to(DEV), hr_prev.to(DEV)
+    out = {}
+    for i in range(frames):
+        lr_curr = clip[i:i + 1]
+        ref = O.frnet_step(p, lr_curr, lr_prev, hr_prev, 4, 'BD')
+        got = net.step(lr_curr.to(DEV), g_lr_prev, g_hr_prev)
+        out[f'rel_l2_f{i}'] = rell2(got.cpu().numpy(), ref.numpy())
+        lr_prev, hr_prev = lr_curr, ref
+        g_lr_prev, g_hr_prev = lr_curr.to(DEV), got
+    mse = float(((got.cpu() - ref) ** 2).mean())
+    out['psnr_vs_ref_db'] = float(10 * np.log10(1.0 / max(mse, 1e-20)))
+    for i in range(frames):
+        assert out[f'rel_l2_f{i}'] <= 1e-3, out
+    return out
+
+
+def check_batch_consistency(n=3, h=24, w=40):
+    """step() on a batch of clips == step() on each clip alone (lock-stepped clips are
+    independent): bit exact."""
+    net, p = _net(15, 4, 'BD', 2.0, nb=2)
+    a, b, c = rand(60, n, 3, h, w).to(DEV), rand(61, n, 3, h, w).to(DEV), rand(62, n, 3, 4 * h, 4 * w).to(DEV)
+    full = net.step(a, b, c)
+    for i in range(n):
+        one = net.step(a[i:i + 1], b[i:i + 1], c[i:i + 1])
+        assert torch.equal(one[0], full[i]), f'clip {i} differs between batch and solo'
+    return {}
+
+
+def check_engine_matches_eager(n=2, t=5, h=24, w=40):
+    """CUDA-graph clip engine == eager step loop, bit exact on the uint8 output."""
+    net, p = _net(16, 4, 'BD', 2.0, nb=3)
+    clips = torch.stack([O.make_clip(70 + i, t, 3, h, w) for i in range(n)])       # n,t,c,h,w
+    got = T.infer_clips(net, clips, torch.device(DEV))
+    lr_prev = torch.zeros(n, 3, h, w, device=DEV)
+    hr_prev = torch.zeros(n, 3, 4 * h, 4 * w, device=DEV)
+    for i in range(t):
+        lr_curr = clips[:, i].to(DEV)
+        hr = net.step(lr_curr, lr_prev, hr_prev)
+        ref_u8 = ops.float_to_uint8_nhwc(hr).cpu().numpy()
+        assert np.array_equal(got[:, i], ref_u8), f'frame {i}'
+        lr_prev, hr_prev = lr_curr, hr
+    assert got.shape == (n, t, 4 * h, 4 * w, 3)
+    return {}
+
+
+CHECKS = {
+    'warp_hrflow_s4': lambda: check_warp_hrflow(4),
+    'warp_hrflow_s2': lambda: check_warp_hrflow(2, h=9, w=70),
+    'warp_lrflow_bd4': lambda: check_warp_lrflow(4, 'BD'),
+    'warp_lrflow_bi2': lambda: check_warp_lrflow(2, 'BI', h=20, w=24),
+    'pool_upsample': check_pool_upsample,
+    'module_ops': check_module_ops,
+    'conv_simt_64': lambda: check_conv('simt'),
+    'conv_simt_pad': lambda: check_conv('simt', cin=64, cout=64, cin_real=51, cout_real=32, act=L.ACT_LRELU02),
+    'conv_simt_convT': lambda: check_conv('simt', kind=L.CONVT_3X3_S2),
+    'conv_simt_res': lambda: check_conv('simt', act=L.ACT_NONE, residual=True),
+    'conv_simt_256': lambda: check_conv('simt', cin=256, cout=128, h=9, w=12),
+    'epilogues_simt': lambda: check_conv_epilogues('simt'),
+    'conv_tc_tap_64': lambda: check_conv('tcgen05', L.AMODE_TAP),
+    'conv_tc_halo_64': lambda: check_conv('tcgen05', L.AMODE_HALO),
+    'conv_tc_halo_res': lambda: check_conv('tcgen05', L.AMODE_HALO, act=L.ACT_NONE, residual=True),
+    'conv_tc_tap_convT': lambda: check_conv('tcgen05', L.AMODE_TAP, kind=L.CONVT_3X3_S2),
+    'conv_tc_halo_convT': lambda: check_conv('tcgen05', L.AMODE_HALO, kind=L.CONVT_3X3_S2),
+    'conv_tc_tap_128_256': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=128, cout=256, h=16, w=40),
+    'conv_tc_tap_256_256': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=256, cout=256, h=16, w=40),
+    'conv_tc_tap_256_128': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=256, cout=128, h=33, w=80, n=1),
+    'conv_tc_auto_pad': lambda: check_conv('tcgen05', None, cin=64, cout=64, cin_real=51, cout_real=32, act=L.ACT_LRELU02),
+    'epilogues_tc': lambda: check_conv_epilogues('tcgen05'),
+    'conv_tc_vs_simt_tap_full': lambda: check_conv_vs_simt(L.AMODE_TAP),
+    'conv_tc_vs_simt_halo_full': lambda: check_conv_vs_simt(L.AMODE_HALO),
+    'conv_tc_vs_simt_halo_convT_full': lambda: check_conv_vs_simt(L.AMODE_HALO, kind=L.CONVT_3X3_S2),
+    'conv_tc_vs_simt_halo_2cta': lambda: check_conv_vs_simt(L.AMODE_HALO, h=64, w=64, n=2, max_ctas=3),
+    'step_golden_g1': lambda: check_step_golden('g1'),
+    'step_golden_g2': lambda: check_step_golden('g2'),
+    'step_bi2_golden': check_step_bi2,
+    'infer_sequence_golden': check_infer_sequence_golden,
+    'forward_sequence_golden': check_forward_sequence_golden,
+    'batch_consistency': check_batch_consistency,
+    'engine_matches_eager': check_engine_matches_eager,
+    'step_vs_oracle_fullsize': check_step_vs_oracle_fullsize,
+}

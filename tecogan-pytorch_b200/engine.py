@@ -55,8 +55,10 @@ class ClipEngine:
             pool = None
             for p in (0, 1):
                 g = torch.cuda.CUDAGraph()
+                before = ops.LAUNCH_COUNT
                 with torch.cuda.graph(g, pool=pool):
                     self._enqueue(p)
+                self.launches_per_step = ops.LAUNCH_COUNT - before
                 pool = g.pool()
                 self.graphs[p] = g
             self.reset()
@@ -72,15 +74,19 @@ class ClipEngine:
         if self.graphs[p] is not None:
             self.graphs[p].replay()
         else:
+            before = ops.LAUNCH_COUNT
             self._enqueue(p)
+            self.launches_per_step = ops.LAUNCH_COUNT - before
 
     def run_clips(self, lr_host, out_host=None):
-        """lr_host: pinned (or pageable) CPU tensor [t,n,c,h,w] fp32 (or a CUDA tensor of that
-        shape); returns pinned uint8 tensor [t,n,H,W,c].  Copies run on side streams and overlap
-        the graph replays; one synchronisation at the end."""
-        t = lr_host.shape[0]
-        if out_host is None:
-            out_host = torch.empty((t, self.n, self.H, self.W, self.c), dtype=torch.uint8).pin_memory()
+        """lr_host: pinned CPU tensor (or CUDA tensor) [n,t,c,h,w] fp32; returns a pinned uint8
+        tensor [t,n,H,W,c].  Per frame: n contiguous H2D copies (one per clip, no host-side
+        transpose), one graph replay, one D2H copy -- on three streams, so the copies overlap the
+        compute of neighbouring frames; one synchronisation at the end."""
+        t = lr_host.shape[1]
+        if out_host is None:   # caching host allocator: cheap after the first call
+            out_host = torch.empty((t, self.n, self.H, self.W, self.c), dtype=torch.uint8,
+                                   pin_memory=True)
         with torch.cuda.device(self.device):
             self.main.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.main):
@@ -95,7 +101,8 @@ class ClipEngine:
                     # lr[p] was last READ by frame i-1 (as lr_prev); wait for that frame
                     if frame_done[p ^ 1] is not None:
                         self.h2d.wait_event(frame_done[p ^ 1])
-                    self.lr[p].copy_(lr_host[i], non_blocking=True)
+                    for k in range(self.n):
+                        self.lr[p][k].copy_(lr_host[k, i], non_blocking=True)
                     in_ready[p] = torch.cuda.Event()
                     in_ready[p].record(self.h2d)
                 with torch.cuda.stream(self.main):
@@ -139,8 +146,10 @@ def infer_clips(net, lr_data, device):
     if device.type != 'cuda':
         raise ops.L.TecoganB200Error('tecogan-b200 runs on CUDA devices only (no CPU path)')
     eng = get_engine(net, n, c, h, w, device)
-    src = lr_data.detach().float().transpose(0, 1).contiguous()      # t,n,c,h,w
+    src = lr_data.detach()
+    if src.dtype != torch.float32:
+        src = src.float()
     if not src.is_cuda and not src.is_pinned():
-        src = src.pin_memory()
+        src = src.pin_memory()           # pageable input: one staging copy (pass pinned to avoid)
     out = eng.run_clips(src)
     return out.numpy().transpose(1, 0, 2, 3, 4)

@@ -12,7 +12,12 @@ import torch
 from . import lib as L
 
 
+LAUNCH_COUNT = 0   # kernels enqueued through the C ABI by this process (each call = 1 launch)
+
+
 def _stream():
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -65,7 +65,7 @@ def test_bicubic_kernel_values():
 
 
 # ------------------------------------------------------------------ FRNet.step
-@pytest.mark.parametrize('tag,gain', [('g1', 1.0), ('g2', 2.0)])
+@pytest.mark.parametrize('tag,gain', [('g1', 1.0), ('g15', 1.5), ('g2', 2.0)])
 def test_step_bd4(tag, gain):
     g = np.load(os.path.join(G, f'step_bd4_18x28_{tag}.npz'))
     p = O.make_frnet_params(11, scale=4, degradation='BD', gain=gain)
@@ -78,8 +78,8 @@ def test_step_bd4(tag, gain):
 
 
 def test_step_bi2():
-    g = np.load(os.path.join(G, 'step_bi2_20x24_g2.npz'))
-    p = O.make_frnet_params(12, scale=2, degradation='BI', gain=2.0)
+    g = np.load(os.path.join(G, 'step_bi2_20x24_g15.npz'))
+    p = O.make_frnet_params(12, scale=2, degradation='BI', gain=1.5)
     assert 'upsample_func.kernels' not in p and 'srnet.conv_up.2.weight' not in p
     assert p['srnet.conv_in.0.weight'].shape == (64, 15, 3, 3)
     hr = O.frnet_step(p, rand(4, 1, 3, 20, 24), rand(5, 1, 3, 20, 24), rand(6, 1, 3, 40, 48), 2, 'BI')
@@ -87,8 +87,8 @@ def test_step_bi2():
 
 
 def test_infer_sequence_uint8():
-    g = np.load(os.path.join(G, 'infer_seq_bd4_16x24_g2.npz'))
-    p = O.make_frnet_params(13, scale=4, degradation='BD', gain=2.0)
+    g = np.load(os.path.join(G, 'infer_seq_bd4_16x24_g15.npz'))
+    p = O.make_frnet_params(13, scale=4, degradation='BD', gain=1.5)
     seq = O.frnet_infer_sequence(p, O.make_clip(7, 4, 3, 16, 24), 4, 'BD')
     assert seq.shape == g['hr_seq'].shape and seq.dtype == np.uint8
     d = np.abs(seq.astype(np.int32) - g['hr_seq'].astype(np.int32))
@@ -96,8 +96,8 @@ def test_infer_sequence_uint8():
 
 
 def test_forward_sequence():
-    g = np.load(os.path.join(G, 'fwd_seq_bd4_16x16_g2.npz'))
-    p = O.make_frnet_params(14, scale=4, degradation='BD', gain=2.0)
+    g = np.load(os.path.join(G, 'fwd_seq_bd4_16x16_g15.npz'))
+    p = O.make_frnet_params(14, scale=4, degradation='BD', gain=1.5)
     d = O.frnet_forward_sequence(p, rand(8, 1, 3, 3, 16, 16), 4, 'BD')
     for k in ('hr_data', 'hr_flow', 'lr_prev', 'lr_curr', 'lr_flow'):
         assert tuple(d[k].shape) == g[k].shape, k
@@ -131,3 +131,37 @@ def test_oracle_vs_live_reference_full_size():
         ref = net.step(lr_curr, lr_prev, hr_prev)
     hr = O.frnet_step(p, lr_curr, lr_prev, hr_prev, 4, 'BD')
     assert relerr(hr.numpy(), ref.numpy()) <= 5e-5
+
+
+# ------------------------------------------------------------------ library-op restatement (bench CPU baseline)
+def test_torchref_matches_oracle_and_golden():
+    from oracle import frnet_torchref as R
+    g = np.load(os.path.join(G, 'step_bd4_18x28_g2.npz'))
+    p = O.make_frnet_params(11, scale=4, degradation='BD', gain=2.0)
+    a, b, c = rand(1, 1, 3, 18, 28), rand(2, 1, 3, 18, 28), rand(3, 1, 3, 72, 112)
+    with torch.no_grad():
+        hr = R.step(p, a, b, c, 4, 'BD')
+    assert relerr(hr.numpy(), g['hr_curr']) <= 2e-5
+    assert relerr(hr.numpy(), O.frnet_step(p, a, b, c, 4, 'BD').numpy()) <= 2e-5
+    g2 = np.load(os.path.join(G, 'step_bi2_20x24_g15.npz'))
+    p2 = O.make_frnet_params(12, scale=2, degradation='BI', gain=1.5)
+    with torch.no_grad():
+        hr2 = R.step(p2, rand(4, 1, 3, 20, 24), rand(5, 1, 3, 20, 24), rand(6, 1, 3, 40, 48), 2, 'BI')
+    assert relerr(hr2.numpy(), g2['hr_curr']) <= 2e-5
+
+
+def test_fp16_precision_model_distance_to_fp32():
+    """The precision model of the CUDA path (fp16 storage, fp32 accumulate) against the fp32
+    reference fixtures: within the 1e-3 north-star bar for PyTorch-default (g1) and 1.5x (g15)
+    weights; the chaotic 2x weights (g2) are outside it by design and are used as a stress case."""
+    from oracle import frnet_fp16emu as E
+    a, b, c = rand(1, 1, 3, 18, 28), rand(2, 1, 3, 18, 28), rand(3, 1, 3, 72, 112)
+    dist = {}
+    for tag, gain in (('g1', 1.0), ('g15', 1.5), ('g2', 2.0)):
+        g = np.load(os.path.join(G, f'step_bd4_18x28_{tag}.npz'))
+        p = O.make_frnet_params(11, scale=4, degradation='BD', gain=gain)
+        with torch.no_grad():
+            hr, _ = E.step(p, a, b, c, 4, 'BD')
+        dist[tag] = float(np.linalg.norm(hr.numpy() - g['hr_curr']) / np.linalg.norm(g['hr_curr']))
+    assert dist['g1'] <= 1e-4 and dist['g15'] <= 1e-3, dist
+    assert 1e-3 < dist['g2'] < 1e-2, dist

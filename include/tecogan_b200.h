@@ -45,7 +45,7 @@ enum { TG_UP_BICUBIC = 0, TG_UP_BILINEAR = 1 };
 enum {
   TG_EPI_NHWC_F16 = 0,      /* y = act(conv + bias) [+ residual]  -> NHWC fp16        */
   TG_EPI_FLOW_NCHW_F32 = 1, /* y = 24*tanh(conv + bias)           -> NCHW fp32 [N,2,H,W] */
-  TG_EPI_OUT_NCHW_F32 = 2   /* y = conv + bias + upsample(aux)    -> NCHW fp32 [N,C,H,W] */
+  TG_EPI_OUT_NCHW_F32 = 2   /* y += conv + bias (y pre-filled)    -> NCHW fp32 [N,C,H,W] */
 };
 enum { TG_AMODE_AUTO = 0, TG_AMODE_HALO = 1, TG_AMODE_TAP = 2 };
 
@@ -72,8 +72,9 @@ int tg_pack_convT3x3s2_weights(const float* w_iohw, int cin, int cout, void* pac
 /* ------------------------------------------------------------------------
  * 3x3 convolution / stride-2 transposed convolution as tcgen05 implicit GEMM.
  * Replaces nn.Conv2d+activation (tecogan_nets.py:23-65, 92-98, 111-116, 131),
- * nn.ConvTranspose2d+ReLU (:119-126), torch.tanh(.)*24 (:80) and
- * `out += upsample_func(lr_curr)` (:145).
+ * nn.ConvTranspose2d+ReLU (:119-126), torch.tanh(.)*24 (:80) and the add of
+ * `out += upsample_func(lr_curr)` (:145): the caller pre-fills y with
+ * tg_upsample_nchw_f32(lr_curr) and TG_EPI_OUT_NCHW_F32 accumulates conv+bias into it.
  * ---------------------------------------------------------------------- */
 typedef struct tg_conv_desc {
   const void* x;        /* NHWC fp16 [n,h,w,cin]                                         */
@@ -81,7 +82,6 @@ typedef struct tg_conv_desc {
   const float* bias;    /* fp32 [cout] (zero padded)                                     */
   const void* residual; /* NHWC fp16 [n,h,w,cout] or NULL (TG_EPI_NHWC_F16, conv3x3 only) */
   void* y;              /* see epilogue; convT writes [n,2h,2w,cout]                     */
-  const float* aux;     /* TG_EPI_OUT_NCHW_F32: lr_curr NCHW fp32 [n,cout_real,h/s,w/s]  */
   int32_t n, h, w;      /* input batch / height / width                                  */
   int32_t cin, cout;    /* stored channel counts: cin in {64,128,256}; cout in {64,128,256}
                            for TG_EPI_NHWC_F16, 16 for the two NCHW epilogues            */
@@ -89,10 +89,9 @@ typedef struct tg_conv_desc {
   int32_t kind;         /* TG_CONV_3X3 | TG_CONVT_3X3_S2                                 */
   int32_t act;          /* TG_ACT_*                                                      */
   int32_t epilogue;     /* TG_EPI_*                                                      */
-  int32_t up_scale;     /* TG_EPI_OUT_NCHW_F32: 2 or 4                                   */
-  int32_t up_mode;      /* TG_EPI_OUT_NCHW_F32: TG_UP_*                                  */
   int32_t a_mode;       /* TG_AMODE_* (tcgen05 kernel only; AUTO = fastest validated)    */
   int32_t max_ctas;     /* 0 = one persistent CTA per SM                                 */
+  int32_t reserved;     /* must be 0                                                     */
 } tg_conv_desc;
 
 int tg_conv_tcgen05(const tg_conv_desc* d, void* stream);

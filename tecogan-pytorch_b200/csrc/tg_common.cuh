@@ -43,17 +43,20 @@ __host__ __device__ static inline uint32_t tg_wtile_off(uint32_t n, uint32_t k) 
 //   acc1: in[y,x]*Wt[1,2] + in[y,x+1]*Wt[1,0]
 //   acc2: in[y,x]*Wt[2,1] + in[y+1,x]*Wt[0,1]
 //   acc3: in[y,x]*Wt[2,2] + in[y,x+1]*Wt[2,0] + in[y+1,x]*Wt[0,2] + in[y+1,x+1]*Wt[0,0]
-struct TgGroup { int8_t acc, dy, dx, ky, kx; };
-__host__ __device__ static inline TgGroup tg_group(int kind, int g) {
-  if (kind == TG_CONV_3X3) {
-    TgGroup r = {0, (int8_t)(g / 3 - 1), (int8_t)(g % 3 - 1), (int8_t)(g / 3), (int8_t)(g % 3)};
-    return r;
+struct TgGroup { int acc, dy, dx, ky, kx; };
+__host__ __device__ constexpr TgGroup tg_group(int kind, int g) {
+  if (kind == TG_CONV_3X3) return TgGroup{0, g / 3 - 1, g % 3 - 1, g / 3, g % 3};
+  switch (g) {
+    case 0: return TgGroup{0, 0, 0, 1, 1};
+    case 1: return TgGroup{1, 0, 0, 1, 2};
+    case 2: return TgGroup{1, 0, 1, 1, 0};
+    case 3: return TgGroup{2, 0, 0, 2, 1};
+    case 4: return TgGroup{2, 1, 0, 0, 1};
+    case 5: return TgGroup{3, 0, 0, 2, 2};
+    case 6: return TgGroup{3, 0, 1, 2, 0};
+    case 7: return TgGroup{3, 1, 0, 0, 2};
+    default: return TgGroup{3, 1, 1, 0, 0};
   }
-  const int8_t T[9][5] = {{0, 0, 0, 1, 1}, {1, 0, 0, 1, 2}, {1, 0, 1, 1, 0}, {2, 0, 0, 2, 1},
-                          {2, 1, 0, 0, 1}, {3, 0, 0, 2, 2}, {3, 0, 1, 2, 0}, {3, 1, 0, 0, 2},
-                          {3, 1, 1, 0, 0}};
-  TgGroup r = {T[g][0], T[g][1], T[g][2], T[g][3], T[g][4]};
-  return r;
 }
 
 // ---------------------------------------------------------------- sampling helpers (device)
@@ -66,6 +69,19 @@ __device__ __forceinline__ void tg_cubic_taps(int d, int s, float k[4]) {
   k[1] = 1.f - (a + 3.f) * t2 + (a + 2.f) * t3;
   k[2] = -a * t + (2.f * a + 3.f) * t2 - (a + 2.f) * t3;
   k[3] = a * t2 - a * t3;
+}
+
+// upsample_func as a separable 4-tap filter over source indices clamp(i-1 .. i+2) (replicate):
+//   bicubic : BicubicUpsampler kernels[d]                           (net_utils.py:116-131)
+//   bilinear: F.interpolate(align_corners=False): src = max((s*i+d+0.5)/s-0.5, 0) falls between
+//             i-1,i (d < s/2) or i,i+1 (d >= s/2) with fraction f; clamping the INDEX is
+//             equivalent to clamping src at 0 / L-1 (both taps hit the same border sample).
+__device__ __forceinline__ void tg_up_taps(int up_mode, int d, int s, float k[4]) {
+  if (up_mode == TG_UP_BICUBIC) { tg_cubic_taps(d, s, k); return; }
+  const float src = ((float)d + 0.5f) / (float)s - 0.5f;      // in (-0.5, 0.5)
+  k[0] = k[1] = k[2] = k[3] = 0.f;
+  if (src < 0.f) { const float f = src + 1.f; k[0] = 1.f - f; k[1] = f; }
+  else           { k[1] = 1.f - src; k[2] = src; }
 }
 
 // reflect index of F.pad(...,'reflect') on the bottom/right only: i in [0, L) over a source of

@@ -43,7 +43,8 @@ struct KParams {
   int halo, b_resident;
   int box_w, box_h, org_x, org_y;
   int n_stages;
-  uint32_t stage_bytes, a_bytes, b_tile_bytes;
+  int n_split, bn;                 // output channels are split over n_split CTAs of bn columns
+  uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
   uint32_t off_b, off_stage, off_staging;
   uint32_t idesc;
 };
@@ -175,6 +176,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t v[16]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// exactly one lane of a converged warp returns 1 (lets ptxas keep warp-uniform operands in
+// uniform registers instead of wrapping every tcgen05 instruction in a divergence loop)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xFFFFFFFF;\nselp.b32 %0, 1, 0, px;\n}\n"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -191,18 +203,21 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t sbo_byte
   return d;
 }
 
-struct TileCoord { int n, y0, x0; };
+struct TileCoord { int n, y0, x0, nb; };
 __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
   TileCoord t;
   const int per_img = p.tiles_x * p.tiles_y;
-  t.n = tile / per_img;
-  const int r = tile - t.n * per_img;
+  const int sp = tile / p.n_split;          // CTAs that share an A tile are adjacent (L2 reuse)
+  t.nb = tile - sp * p.n_split;
+  t.n = sp / per_img;
+  const int r = sp - t.n * per_img;
   t.y0 = (r / p.tiles_x) * TH;
   t.x0 = (r % p.tiles_x) * TW;
   return t;
 }
 
 // ------------------------------------------------------------------ the kernel
+template <int KIND, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_y0,
@@ -226,7 +241,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 48);
   float* bias_s = reinterpret_cast<float*>(sm + 1024);
 
-  const int epi_warps_active = (d.cout >= 64) ? 8 : 4;
+  const int epi_warps_active = (p.bn >= 64) ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -271,7 +286,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
-        if (p.halo) {
+        if (HALO) {
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
             mbar_expect_tx(bar_full + 8 * stage, p.a_bytes);
@@ -280,16 +295,19 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
+#pragma unroll
           for (int g = 0; g < 9; ++g) {
-            const TgGroup gr = tg_group(d.kind, g);
+            constexpr int kDummy = 0; (void)kDummy;
+            const TgGroup gr = tg_group(KIND, g);
             for (int c = 0; c < p.chunks; ++c) {
               mbar_wait(bar_empty + 8 * stage, phase ^ 1, 2);
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
-              mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + (p.b_resident ? 0u : p.b_tile_bytes));
+              mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
               tma_load_4d(sa, &map_a, bar_full + 8 * stage, c * 64, tc.x0 + gr.dx, tc.y0 + gr.dy, tc.n);
               if (!p.b_resident)
-                bulk_load(sa + kTapABytes, wglob + (size_t)(g * p.chunks + c) * p.b_tile_bytes,
-                          p.b_tile_bytes, bar_full + 8 * stage);
+                bulk_load(sa + kTapABytes,
+                          wglob + (size_t)(g * p.chunks + c) * p.b_tile_bytes + (size_t)tc.nb * p.b_stage_bytes,
+                          p.b_stage_bytes, bar_full + 8 * stage);
               if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -297,62 +315,79 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       }
     }
   } else if (warp == 1) {
-    // ============================================================ MMA issuer (single thread)
-    if (lane == 0) {
+    // ============================================================ MMA issuer
+    // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the MMAs.
+    {
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      const uint32_t acc_stride = (uint32_t)(p.n_acc * d.cout);
+      const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
+      // descriptor templates: everything but the 14-bit start address is constant per kernel
+      constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
+      constexpr int kOrg = (KIND == TG_CONV_3X3) ? -1 : 0;
+      const uint64_t a_hi = make_sdesc(0, HALO ? (uint32_t)kBoxW * 128u : 1024u);
+      const uint64_t b_hi = make_sdesc(0, 1024u);
+      const uint32_t btb16 = p.b_tile_bytes >> 4;
+      const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
         tc_fence_after();
         const uint32_t d_base = tmem_base + buf * acc_stride;
-        uint32_t written = 0;   // bit a: accumulator a already holds a partial sum
-        if (p.halo) {
-          const uint32_t sbo = (uint32_t)p.box_w * 128u;
+        if (HALO) {
           for (int c = 0; c < p.chunks; ++c) {
             mbar_wait(bar_full + 8 * stage, phase, 5);
             tc_fence_after();
-            const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
-            for (int g = 0; g < 9; ++g) {
-              const TgGroup gr = tg_group(d.kind, g);
-              const uint32_t a_addr = sa + (uint32_t)((gr.dy - p.org_y) * p.box_w + (gr.dx - p.org_x)) * 128u;
-              const uint32_t b_addr = smem_b + (uint32_t)(g * p.chunks + c) * p.b_tile_bytes;
+            const uint32_t sa16 = ((smem_stage0 + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
+            if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(d_base + gr.acc * d.cout, make_sdesc(a_addr + k * 32, sbo),
-                         make_sdesc(b_addr + k * 32, 1024), p.idesc, (written >> gr.acc) & 1u);
-                written |= 1u << gr.acc;
-              }
+            for (int g = 0; g < 9; ++g) {
+              constexpr int kUnused = 0; (void)kUnused;
+              const TgGroup gr = tg_group(KIND, g);
+              // first MMA into an accumulator (per tile) overwrites, the rest accumulate
+              const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
+              const uint32_t a16 = sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
+              const uint32_t b16 = smem_b16 + (uint32_t)(g * p.chunks + c) * btb16;
+              const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
+                         (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
             }
             umma_commit(bar_empty + 8 * stage);
+            }
+            __syncwarp();
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
+#pragma unroll
           for (int g = 0; g < 9; ++g) {
-            const TgGroup gr = tg_group(d.kind, g);
+            const TgGroup gr = tg_group(KIND, g);
+            const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
+            const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
             for (int c = 0; c < p.chunks; ++c) {
               mbar_wait(bar_full + 8 * stage, phase, 6);
               tc_fence_after();
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
-              const uint32_t b_addr = p.b_resident
-                                          ? smem_b + (uint32_t)(g * p.chunks + c) * p.b_tile_bytes
-                                          : sa + kTapABytes;
+              const uint32_t a16 = (sa & 0x3FFFFu) >> 4;
+              const uint32_t b16 = p.b_resident ? smem_b16 + (uint32_t)(g * p.chunks + c) * btb16
+                                                : ((sa + kTapABytes) & 0x3FFFFu) >> 4;
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_f16(d_base + gr.acc * d.cout, make_sdesc(sa + k * 32, 1024),
-                         make_sdesc(b_addr + k * 32, 1024), p.idesc, (written >> gr.acc) & 1u);
-                written |= 1u << gr.acc;
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
+                           (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
+                umma_commit(bar_empty + 8 * stage);
               }
-              umma_commit(bar_empty + 8 * stage);
+              __syncwarp();
               if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
             }
           }
         }
-        umma_commit(bar_tfull + 8 * buf);
+        if (elect_one_sync()) umma_commit(bar_tfull + 8 * buf);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -360,12 +395,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     const int ew = warp - 4;
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int half = ew >> 2;      // column half
-    const bool active = (d.cout >= 64) || half == 0;
-    const int cols_per_half = (d.cout >= 64) ? d.cout / 2 : d.cout;
+    const bool active = (p.bn >= 64) || half == 0;
+    const int cols_per_half = (p.bn >= 64) ? p.bn / 2 : p.bn;
     const int r = q * 32 + lane;   // row of the tile = TMEM lane
     const int ty = r >> 3, tx = r & 7;
-    const uint32_t acc_stride = (uint32_t)(p.n_acc * d.cout);
-    const int chunks_out = d.cout / 64;
+    const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
+    const int chunks_out = p.bn / 64;
     const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -387,13 +422,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             for (int pc = 0; pc < pieces; ++pc) {
               const int col0 = half * cols_per_half + pc * 32;
               uint32_t v[32];
-              tmem_ld32(tmem_base + buf * acc_stride + acc * d.cout + col0 + ((uint32_t)(q * 32) << 16), v);
+              tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + col0 + ((uint32_t)(q * 32) << 16), v);
               uint4 res[4];
               const bool has_res = (d.residual != nullptr) && inb;
               if (has_res) {
                 const uint4* rp = reinterpret_cast<const uint4*>(
                     reinterpret_cast<const __half*>(d.residual) +
-                    (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + col0);
+                    (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn + col0);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
               }
@@ -413,8 +448,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int cidx = i * 8 + j * 2;
-                  float a0 = tg_epi_val(__uint_as_float(v[cidx]), bias_s[col0 + cidx], d.act);
-                  float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bias_s[col0 + cidx + 1], d.act);
+                  float a0 = tg_epi_val(__uint_as_float(v[cidx]), bias_s[tc.nb * p.bn + col0 + cidx], d.act);
+                  float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bias_s[tc.nb * p.bn + col0 + cidx + 1], d.act);
                   if (has_res) {
                     const float2 rf = __half22float2(rh[j]);
                     a0 += rf.x; a1 += rf.y;
@@ -450,7 +485,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
           for (int acc = 0; acc < p.n_acc; ++acc)
             for (int cc = 0; cc < chunks_out; ++cc)
               tma_store_4d(ymaps[acc], base + p.off_staging + (uint32_t)(acc * chunks_out + cc) * 16384u,
-                           cc * 64, tc.x0, tc.y0, tc.n);
+                           tc.nb * p.bn + cc * 64, tc.x0, tc.y0, tc.n);
           bulk_commit();
         }
       }
@@ -524,12 +559,6 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who) {
     TG_REQUIRE(d->kind == TG_CONV_3X3 && d->cout == 16 && d->cout_real >= 1 && d->cout_real <= 4,
                TG_E_UNSUPPORTED, "%s: NCHW epilogues need conv3x3, cout=16, cout_real<=4", who);
     TG_REQUIRE(d->residual == nullptr, TG_E_UNSUPPORTED, "%s: residual with NCHW epilogue", who);
-    if (d->epilogue == TG_EPI_OUT_NCHW_F32) {
-      TG_REQUIRE(d->aux != nullptr, TG_E_INVALID, "%s: aux (lr_curr) is null", who);
-      TG_REQUIRE((d->up_scale == 2 || d->up_scale == 4) && d->h % d->up_scale == 0 &&
-                     d->w % d->up_scale == 0, TG_E_INVALID, "%s: up_scale", who);
-      TG_REQUIRE(d->up_mode == TG_UP_BICUBIC || d->up_mode == TG_UP_BILINEAR, TG_E_INVALID, "%s: up_mode", who);
-    }
   } else {
     TG_REQUIRE(false, TG_E_INVALID, "%s: epilogue %d", who, d->epilogue);
   }
@@ -551,24 +580,36 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.chunks = d->cin / 64;
   p.n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
-  p.idesc = (1u << 4) | ((uint32_t)(d->cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   const uint32_t b_total = 9u * p.chunks * p.b_tile_bytes;
-  const uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? (uint32_t)p.n_acc * (d->cout / 64) * 16384u : 0u;
+  uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? (uint32_t)p.n_acc * (d->cout / 64) * 16384u : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
   const uint32_t halo_stage = (halo_bytes + 1023u) & ~1023u;
-  const uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
+  uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
 
   const bool can_resident_halo = fixed + b_total + 2u * halo_stage <= kSmemLimit;
-  const bool can_resident_tap = fixed + b_total + 2u * kTapABytes <= kSmemLimit;
+  // cout > 64 only occurs on the low-resolution FNet layers: few spatial tiles, so stream the
+  // weights and split N over CTAs instead of making every CTA load all of them
+  const bool can_resident_tap = d->cout <= 64 && fixed + b_total + 2u * kTapABytes <= kSmemLimit;
   int mode = d->a_mode;
   if (mode == TG_AMODE_AUTO) mode = can_resident_halo ? TG_AMODE_HALO : TG_AMODE_TAP;
   TG_REQUIRE(!(mode == TG_AMODE_HALO && !can_resident_halo), TG_E_UNSUPPORTED,
              "conv_tcgen05: halo mode needs the weights resident in smem (cin=%d cout=%d)", d->cin, d->cout);
   p.halo = mode == TG_AMODE_HALO;
   p.b_resident = p.halo ? 1 : (can_resident_tap ? 1 : 0);
+  // streamed weights: split the output channels over CTAs of 64 columns -> cout/64 x more CTAs on
+  // the low-resolution FNet layers, each streaming 1/(cout/64) of the weights
+  p.n_split = (!p.b_resident && d->cout > 64) ? d->cout / 64 : 1;
+  p.bn = d->cout / p.n_split;
+  p.b_stage_bytes = (uint32_t)p.bn * 128u;
+  p.num_tiles *= p.n_split;
+  p.idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (d->epilogue == TG_EPI_NHWC_F16) {
+    staging = (uint32_t)p.n_acc * (p.bn / 64) * 16384u;
+    fixed = 1024u + kHeaderBytes + staging;
+  }
   if (p.halo) {
     p.box_w = hbox_w; p.box_h = hbox_h;
     p.org_x = d->kind == TG_CONV_3X3 ? -1 : 0;
@@ -578,7 +619,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   } else {
     p.box_w = TW; p.box_h = TH; p.org_x = 0; p.org_y = 0;
     p.a_bytes = kTapABytes;
-    p.stage_bytes = kTapABytes + (p.b_resident ? 0u : p.b_tile_bytes);
+    p.stage_bytes = kTapABytes + (p.b_resident ? 0u : p.b_stage_bytes);
   }
   const uint32_t avail = kSmemLimit - fixed - (p.b_resident ? b_total : 0u);
   int stages = (int)(avail / p.stage_bytes);
@@ -620,8 +661,14 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kSmemLimit);
+    cudaError_t e;
+#define TG_SET_ATTR(K, H)                                                                          \
+    e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)kSmemLimit);                                                     \
+    if (e != cudaSuccess) attr_err = e;
+    TG_SET_ATTR(TG_CONV_3X3, true) TG_SET_ATTR(TG_CONV_3X3, false)
+    TG_SET_ATTR(TG_CONVT_3X3_S2, true) TG_SET_ATTR(TG_CONVT_3X3_S2, false)
+#undef TG_SET_ATTR
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_tcgen05: cudaFuncSetAttribute: %s",
              cudaGetErrorString(attr_err));
@@ -633,8 +680,14 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   if (grid > p.num_tiles) grid = p.num_tiles;
   // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
   // allocation can never contend
-  conv_tcgen05_kernel<<<grid, kThreads, kSmemLimit, (cudaStream_t)stream>>>(map_a, map_y[0], map_y[1],
-                                                                           map_y[2], map_y[3], p);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->kind == TG_CONV_3X3) {
+    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, true><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    else        conv_tcgen05_kernel<TG_CONV_3X3, false><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+  } else {
+    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, true><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, false><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+  }
   TG_CUDA_LAUNCH_CHECK("conv_tcgen05");
   return TG_OK;
 }

@@ -17,12 +17,6 @@ namespace {
 // Warp arithmetic follows net_utils.py:50-82 in closed form: sample at (X+u, Y+v), clamp to
 // the border, x1=min(x0+1,W-1)  (SURVEY.md 8-a4).
 // =====================================================================================
-template <int S>
-struct WarpTile {
-  static constexpr int kThreads = 128;
-  static constexpr int kLrw = kThreads / S;
-};
-
 __device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, int H, int W,
                                                float fx, float fy) {
   fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
@@ -39,16 +33,27 @@ __device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, 
          v11 * ax * ay;
 }
 
+// One CTA = one LR row x LRW=128/S LR pixels = S HR rows x 128 HR columns; 128*S threads, thread
+// (X = tid%128, sy = tid/128) owns ONE HR pixel: 2 flow values, then 4 corner gathers per channel
+// (low register count -> full occupancy, ~14 independent loads in flight per thread).
+//   LRFLOW: the LR flow neighbourhood (4 rows x LRW+3 cols, reflect-padded + replicate-clamped) is
+//   staged in smem once, the x-pass of the separable 4-tap upsampler is evaluated once per
+//   (LR row, HR column) and shared by the S HR rows, the y-pass per thread.
 template <int S, bool LRFLOW>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128 * S)
 warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                        const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
                        int w, int h8, int w8, int up_mode, int cpad) {
-  constexpr int LRW = WarpTile<S>::kLrw;
+  constexpr int LRW = 128 / S;
+  constexpr int NT = 128 * S;
+  constexpr int FW = LRW + 3;                 // LR columns x0-1 .. x0+LRW+1
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* tile = reinterpret_cast<__half*>(smem_raw);  // [LRW][cpad]
+  __shared__ float fsrc[LRFLOW ? 2 * 4 * FW : 1];      // [comp][row i][col]
+  __shared__ float hpass[LRFLOW ? 2 * 4 * 128 : 1];    // [comp][row i][X]
 
-  const int t = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int t = tid & 127, sy = tid >> 7;
   const int x0 = blockIdx.x * LRW;      // first LR column of the tile
   const int y = blockIdx.y;             // LR row
   const int n = blockIdx.z;
@@ -58,11 +63,11 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
 
   // zero the pad channels [ (S*S+1)*C, cpad ) and stage lr_curr
   const int used = (S * S + 1) * C;
-  for (int i = t; i < LRW * (cpad - used); i += 128) {
+  for (int i = tid; i < LRW * (cpad - used); i += NT) {
     const int p = i / (cpad - used), k = i - p * (cpad - used);
     tile[p * cpad + used + k] = __float2half(0.f);
   }
-  for (int i = t; i < LRW * C; i += 128) {
+  for (int i = tid; i < LRW * C; i += NT) {
     const int k = i / LRW, p = i - k * LRW;
     const int xx = x0 + p;
     float v = 0.f;
@@ -70,36 +75,43 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
     tile[p * cpad + k] = __float2half(v);
   }
 
-  if (X < W) {
-    float u[S], v[S];
-    if (LRFLOW) {
-      // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
-      const float* f0 = flow + ((size_t)n * 2 + 0) * h8 * w8;
-      const float* f1 = flow + ((size_t)n * 2 + 1) * h8 * w8;
-#pragma unroll
-      for (int sy = 0; sy < S; ++sy) {
-        u[sy] = (float)S * tg_upsample_at(f0, h8, w8, h, w, S, up_mode, y * S + sy, X);
-        v[sy] = (float)S * tg_upsample_at(f1, h8, w8, h, w, S, up_mode, y * S + sy, X);
-      }
-    } else {
-      const float* f0 = flow + (((size_t)n * 2 + 0) * H + (size_t)y * S) * W + X;
-      const float* f1 = flow + (((size_t)n * 2 + 1) * H + (size_t)y * S) * W + X;
-#pragma unroll
-      for (int sy = 0; sy < S; ++sy) {
-        u[sy] = __ldg(f0 + (size_t)sy * W);
-        v[sy] = __ldg(f1 + (size_t)sy * W);
-      }
+  float u = 0.f, v = 0.f;
+  if (LRFLOW) {
+    // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
+    for (int i = tid; i < 2 * 4 * FW; i += NT) {
+      const int col = i % FW, row = (i / FW) & 3, comp = i / (4 * FW);
+      const int yy = tg_reflect_hi(tg_clampi(y - 1 + row, 0, h - 1), h8);
+      const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), w8);
+      fsrc[i] = __ldg(flow + (((size_t)n * 2 + comp) * h8 + yy) * w8 + xx);
     }
-#pragma unroll
-    for (int sy = 0; sy < S; ++sy) {
-      const float fx = (float)X + u[sy];
-      const float fy = (float)(y * S + sy) + v[sy];
-      // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
-      __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
-      for (int k = 0; k < C; ++k) {
-        const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
-        dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
-      }
+    __syncthreads();
+    for (int i = tid; i < 2 * 4 * 128; i += NT) {
+      const int xcol = i & 127, row = (i >> 7) & 3, comp = i >> 9;
+      float kx[4];
+      tg_up_taps(up_mode, xcol % S, S, kx);
+      const float* f = fsrc + (comp * 4 + row) * FW + xcol / S;   // taps at LR cols lx-1 .. lx+2
+      hpass[i] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
+    }
+    __syncthreads();
+    float ky[4];
+    tg_up_taps(up_mode, sy, S, ky);
+    u = (float)S * (ky[0] * hpass[0 * 128 + t] + ky[1] * hpass[1 * 128 + t] +
+                    ky[2] * hpass[2 * 128 + t] + ky[3] * hpass[3 * 128 + t]);
+    v = (float)S * (ky[0] * hpass[4 * 128 + t] + ky[1] * hpass[5 * 128 + t] +
+                    ky[2] * hpass[6 * 128 + t] + ky[3] * hpass[7 * 128 + t]);
+  } else if (X < W) {
+    const size_t o = ((size_t)y * S + sy) * W + X;
+    u = __ldg(flow + ((size_t)n * 2 + 0) * H * W + o);
+    v = __ldg(flow + ((size_t)n * 2 + 1) * H * W + o);
+  }
+  if (X < W) {
+    const float fx = (float)X + u;
+    const float fy = (float)(y * S + sy) + v;
+    // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
+    __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
+    for (int k = 0; k < C; ++k) {
+      const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
+      dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
     }
   }
   __syncthreads();
@@ -109,7 +121,7 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
   const int vec_per_px = cpad / 8;  // uint4 per pixel
   const uint4* src = reinterpret_cast<const uint4*>(tile);
   uint4* dstg = reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0) * cpad);
-  for (int i = t; i < npx * vec_per_px; i += 128) dstg[i] = src[i];
+  for (int i = tid; i < npx * vec_per_px; i += NT) dstg[i] = src[i];
 }
 
 // =====================================================================================
@@ -260,17 +272,43 @@ __global__ void space_to_depth_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
-__global__ void upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int nc,
-                                     int hin, int win, int h, int w, int s, int up_mode,
-                                     float mul) {
-  const int H = h * s, W = w * s;
-  const size_t total = (size_t)nc * H * W;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int X = (int)(i % W);
-    const int Y = (int)((i / W) % H);
-    const size_t pl = i / ((size_t)H * W);
-    y[i] = mul * tg_upsample_at(x + pl * hin * win, hin, win, h, w, s, up_mode, Y, X);
+// y = mul * upsample_func(reflect_pad(x)): one CTA = one LR row x 128/S LR pixels of one plane ->
+// S HR rows x 128 HR columns; separable 4-tap filter through shared memory (see tg_up_taps).
+template <int S>
+__global__ void __launch_bounds__(128 * S)
+upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int hin, int win, int h,
+                     int w, int up_mode, float mul) {
+  constexpr int LRW = 128 / S;
+  constexpr int FW = LRW + 3;
+  __shared__ float fsrc[4 * FW];
+  __shared__ float hpass[4 * 128];
+  const int tid = threadIdx.x, t = tid & 127, sy = tid >> 7;
+  const int x0 = blockIdx.x * LRW, yl = blockIdx.y;
+  const size_t pl = blockIdx.z;
+  const float* src = x + pl * hin * win;
+  for (int i = tid; i < 4 * FW; i += 128 * S) {
+    const int col = i % FW, row = i / FW;
+    const int yy = tg_reflect_hi(tg_clampi(yl - 1 + row, 0, h - 1), hin);
+    const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), win);
+    fsrc[i] = __ldg(src + (size_t)yy * win + xx);
+  }
+  __syncthreads();
+  {
+    // x-pass: 4 LR rows x 128 HR columns, 128*S threads -> 4/S rows per thread
+    float kx[4];
+    tg_up_taps(up_mode, t % S, S, kx);
+    for (int row = sy; row < 4; row += S) {
+      const float* f = fsrc + row * FW + t / S;
+      hpass[row * 128 + t] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
+    }
+  }
+  __syncthreads();
+  const int X = x0 * S + t;
+  if (X < w * S) {
+    float ky[4];
+    tg_up_taps(up_mode, sy, S, ky);
+    const float v = ky[0] * hpass[t] + ky[1] * hpass[128 + t] + ky[2] * hpass[256 + t] + ky[3] * hpass[384 + t];
+    y[(pl * h * S + (size_t)yl * S + sy) * ((size_t)w * S) + X] = mul * v;
   }
 }
 
@@ -325,11 +363,11 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   const size_t smem = (size_t)lrw * cpad * sizeof(__half);
   __half* o = (__half*)out;
   if (s == 4) {
-    if (lrflow) warp_s2d_concat_kernel<4, true><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<4, false><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) warp_s2d_concat_kernel<4, true><<<grid, 512, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<4, false><<<grid, 512, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   } else {
-    if (lrflow) warp_s2d_concat_kernel<2, true><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<2, false><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) warp_s2d_concat_kernel<2, true><<<grid, 256, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<2, false><<<grid, 256, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   }
   TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
   return TG_OK;
@@ -431,13 +469,15 @@ int tg_space_to_depth_nchw_f32(const float* x, float* y, int n, int c, int h, in
 int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int win, int h, int w,
                          int s, int up_mode, float mul, void* stream) {
   TG_REQUIRE(x && y, TG_E_INVALID, "upsample: null pointer");
-  TG_REQUIRE(n > 0 && c > 0 && hin > 0 && win > 0 && h >= hin && w >= win && s >= 1, TG_E_INVALID,
+  TG_REQUIRE(n > 0 && c > 0 && hin > 0 && win > 0 && h >= hin && w >= win, TG_E_INVALID,
              "upsample: bad shape");
   TG_REQUIRE((h - hin) < hin && (w - win) < win, TG_E_INVALID, "upsample: reflect pad too large");
   TG_REQUIRE(up_mode == TG_UP_BICUBIC || up_mode == TG_UP_BILINEAR, TG_E_INVALID, "upsample: up_mode");
-  const size_t total = (size_t)n * c * h * s * w * s;
-  upsample_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, y, n * c, hin, win, h, w, s, up_mode, mul);
+  TG_REQUIRE(s == 2 || s == 4, TG_E_UNSUPPORTED, "upsample: scale %d (2 or 4)", s);
+  TG_REQUIRE(h <= 65535 && (size_t)n * c <= 65535, TG_E_UNSUPPORTED, "upsample: grid too large");
+  dim3 grid(tg_ceil_div(w, 128 / s), h, n * c);
+  if (s == 4) upsample_nchw_kernel<4><<<grid, 512, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
+  else        upsample_nchw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
   TG_CUDA_LAUNCH_CHECK("upsample");
   return TG_OK;
 }

@@ -11,15 +11,14 @@ __device__ __forceinline__ void tg_epi_flow(const tg_conv_desc& d, int n, int y,
         24.f * tanhf(acc + __ldg(d.bias + ch));
 }
 
-// TG_EPI_OUT_NCHW_F32: conv_out(...) + upsample_func(lr_curr) (tecogan_nets.py:144-145)
+// TG_EPI_OUT_NCHW_F32: out = conv_out(...) ; out += upsample_func(lr_curr) (tecogan_nets.py:144-145).
+// y already holds upsample_func(lr_curr) (tg_upsample_nchw_f32); fp32 add is commutative, so
+// (conv + bias) + up is the reference's value.
 __device__ __forceinline__ void tg_epi_out(const tg_conv_desc& d, int n, int y, int x, int H,
                                            int W, int ch, float acc) {
   if (ch < d.cout_real) {
-    const int s = d.up_scale, h = H / s, w = W / s;
-    const float* plane = d.aux + ((size_t)n * d.cout_real + ch) * h * w;
-    const float up = tg_upsample_at(plane, h, w, h, w, s, d.up_mode, y, x);
-    reinterpret_cast<float*>(d.y)[(((size_t)n * d.cout_real + ch) * H + y) * W + x] =
-        (acc + __ldg(d.bias + ch)) + up;
+    float* o = reinterpret_cast<float*>(d.y) + (((size_t)n * d.cout_real + ch) * H + y) * W + x;
+    *o = (acc + __ldg(d.bias + ch)) + *o;
   }
 }
 

@@ -24,11 +24,11 @@ class ConvDesc(ctypes.Structure):
     """struct tg_conv_desc"""
     _fields_ = [
         ('x', c_void_p), ('weights', c_void_p), ('bias', c_void_p), ('residual', c_void_p),
-        ('y', c_void_p), ('aux', c_void_p),
+        ('y', c_void_p),
         ('n', c_int32), ('h', c_int32), ('w', c_int32),
         ('cin', c_int32), ('cout', c_int32), ('cout_real', c_int32),
         ('kind', c_int32), ('act', c_int32), ('epilogue', c_int32),
-        ('up_scale', c_int32), ('up_mode', c_int32), ('a_mode', c_int32), ('max_ctas', c_int32),
+        ('a_mode', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
     ]
 
 

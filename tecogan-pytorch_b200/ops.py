@@ -96,15 +96,17 @@ class PackedConv:
             return (n, h, w, self.cout), torch.float16
         return (n, self.cout_real, h, w), torch.float32
 
-    def __call__(self, x, y=None, residual=None, aux=None, up_scale=0, up_mode=0, impl=None,
-                 a_mode=None, max_ctas=0):
-        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None)."""
+    def __call__(self, x, y=None, residual=None, impl=None, a_mode=None, max_ctas=0):
+        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None; EPI_OUT accumulates into y, which
+        the caller must have pre-filled)."""
         _req(x, torch.float16, 'conv input', 4)
         n, h, w, cin = x.shape
         if cin != self.cin:
             raise L.TecoganB200Error(f'conv input has {cin} channels, layer expects {self.cin}')
         shape, dtype = self.out_shape(n, h, w)
         if y is None:
+            if self.epilogue == L.EPI_OUT_NCHW_F32:
+                raise L.TecoganB200Error('EPI_OUT_NCHW_F32 accumulates into y: pass a pre-filled y')
             y = torch.empty(shape, dtype=dtype, device=x.device)
         else:
             _req(y, dtype, 'conv output')
@@ -114,16 +116,12 @@ class PackedConv:
             _req(residual, torch.float16, 'residual', 4)
             if tuple(residual.shape) != (n, h, w, self.cout):
                 raise L.TecoganB200Error('residual shape mismatch')
-        if aux is not None:
-            _req(aux, torch.float32, 'aux', 4)
         d = L.ConvDesc()
         d.x, d.weights, d.bias = x.data_ptr(), self.packed.data_ptr(), self.bias.data_ptr()
         d.residual = residual.data_ptr() if residual is not None else None
         d.y = y.data_ptr()
-        d.aux = aux.data_ptr() if aux is not None else None
         d.n, d.h, d.w, d.cin, d.cout, d.cout_real = n, h, w, self.cin, self.cout, self.cout_real
         d.kind, d.act, d.epilogue = self.kind, self.act, self.epilogue
-        d.up_scale, d.up_mode = up_scale, up_mode
         d.a_mode = default_a_mode() if a_mode is None else a_mode
         d.max_ctas = max_ctas
         impl = impl or default_conv_impl()

@@ -231,8 +231,8 @@ def check_conv_epilogues(impl='tcgen05'):
         b = rand(55, 3, lo=-0.1, hi=0.1)
         lr = rand(56, 1, 3, 6, 10)
         pc = ops.PackedConv(wt.to(DEV), b.to(DEV), L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
-        y = pc(nhwc(x), aux=lr.to(DEV), up_scale=s, impl=impl,
-               up_mode=L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR).cpu()
+        base = ops.upsample(lr.to(DEV), s, L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR)
+        y = pc(nhwc(x), y=base, impl=impl).cpu()
         up = K.bicubic_upsample(lr.numpy(), s) if mode == 'BD' else K.bilinear_upsample(lr.numpy(), s)
         ref = F.conv2d(f16(x), f16(wt), b, padding=1) + torch.from_numpy(up)
         out[f'out_{mode}{s}_rel'] = relmax(y.numpy(), ref.numpy())
@@ -416,6 +416,8 @@ CHECKS = {
     'conv_tc_tap_128_256': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=128, cout=256, h=16, w=40),
     'conv_tc_tap_256_256': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=256, cout=256, h=16, w=40),
     'conv_tc_tap_256_128': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=256, cout=128, h=33, w=80, n=1),
+    'conv_tc_tap_64_128': lambda: check_conv('tcgen05', None, cin=64, cout=128, h=33, w=80, n=2),
+    'conv_tc_nsplit_res': lambda: check_conv('tcgen05', None, cin=128, cout=128, h=17, w=20, act=L.ACT_NONE, residual=True),
     'conv_tc_auto_pad': lambda: check_conv('tcgen05', None, cin=64, cout=64, cin_real=51, cout_real=32, act=L.ACT_LRELU02),
     'epilogues_tc': lambda: check_conv_epilogues('tcgen05'),
     'conv_tc_vs_simt_tap_full': lambda: check_conv_vs_simt(L.AMODE_TAP),

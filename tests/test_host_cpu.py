@@ -42,9 +42,9 @@ def test_library_exports_every_header_symbol():
 
 
 def test_conv_desc_struct_layout_matches_header():
-    # 6 pointers + 13 int32 (see struct tg_conv_desc)
-    assert ctypes.sizeof(L.ConvDesc) == 6 * 8 + 13 * 4 + 4   # + tail padding to 8
-    assert L.ConvDesc.n.offset == 48 and L.ConvDesc.max_ctas.offset == 48 + 12 * 4
+    # 5 pointers + 12 int32 (see struct tg_conv_desc)
+    assert ctypes.sizeof(L.ConvDesc) == 5 * 8 + 12 * 4
+    assert L.ConvDesc.n.offset == 40 and L.ConvDesc.max_ctas.offset == 40 + 10 * 4
 
 
 def test_null_and_bad_arguments_are_rejected_without_a_gpu():

@@ -146,6 +146,14 @@ int tg_nhwc_f16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w,
  * x NCHW fp32 [n,c,h,w] -> uint8 [n,h,w,c], round-half-even, clip [0,255] */
 int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int w, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Diagnostics: when a device buffer of 16*gridDim uint64 is registered, every
+ * tg_conv_tcgen05 launch writes per-CTA role timers (cycles spent by the TMA
+ * producer / MMA issuer / epilogue in each wait and work phase) into it.
+ * NULL (default) disables timing. Layout: tools/conv_timers.py.
+ * ---------------------------------------------------------------------- */
+int tg_debug_set_conv_timers(void* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,15 @@ struct KParams {
   uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
   uint32_t off_b, off_stage, off_staging;
   uint32_t idesc;
+  unsigned long long* dbg;         // optional per-CTA role timers (tg_debug_set_conv_timers), else null
 };
+
+// role-timer slots (cycles, per CTA): see tools/conv_timers.py
+enum { T_PROD_WAIT_EMPTY = 0, T_MMA_WAIT_TEMPTY, T_MMA_WAIT_FULL, T_MMA_ISSUE, T_MMA_TOTAL,
+       T_EPI_WAIT_STORE, T_EPI_WAIT_TFULL, T_EPI_COMPUTE, T_EPI_STORE, T_EPI_TOTAL, T_KERNEL, T_PROLOGUE,
+       T_TILES, T_SLOTS = 16 };
+#define TG_T0() (timing ? clock64() : 0)
+#define TG_ACC(var, t0) do { if (timing) var += clock64() - (t0); } while (0)
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -231,6 +239,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const tg_conv_desc& d = p.d;
+  const bool timing = p.dbg != nullptr;
+  const long long t_kernel0 = timing ? clock64() : 0;
 
   // header: barriers
   const uint32_t bar_full = base;                       // [kMaxStages]
@@ -268,6 +278,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  if (timing && threadIdx.x == 0) p.dbg[blockIdx.x * T_SLOTS + T_PROLOGUE] = clock64() - t_kernel0;
 
   const uint32_t smem_b = base + p.off_b;
   const uint32_t smem_stage0 = base + p.off_stage;
@@ -284,11 +295,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       int stage = 0;
       uint32_t phase = 0;
+      long long tw = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
         if (HALO) {
           for (int c = 0; c < p.chunks; ++c) {
+            const long long t0 = TG_T0();
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+            TG_ACC(tw, t0);
             mbar_expect_tx(bar_full + 8 * stage, p.a_bytes);
             tma_load_4d(smem_stage0 + stage * p.stage_bytes, &map_a, bar_full + 8 * stage, c * 64,
                         tc.x0 + p.org_x, tc.y0 + p.org_y, tc.n);
@@ -300,7 +314,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             constexpr int kDummy = 0; (void)kDummy;
             const TgGroup gr = tg_group(KIND, g);
             for (int c = 0; c < p.chunks; ++c) {
+              const long long t0 = TG_T0();
               mbar_wait(bar_empty + 8 * stage, phase ^ 1, 2);
+              TG_ACC(tw, t0);
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
               mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
               tma_load_4d(sa, &map_a, bar_full + 8 * stage, c * 64, tc.x0 + gr.dx, tc.y0 + gr.dy, tc.n);
@@ -313,6 +329,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
       }
+      if (timing) p.dbg[blockIdx.x * T_SLOTS + T_PROD_WAIT_EMPTY] = tw;
     }
   } else if (warp == 1) {
     // ============================================================ MMA issuer
@@ -330,17 +347,28 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint64_t b_hi = make_sdesc(0, 1024u);
       const uint32_t btb16 = p.b_tile_bytes >> 4;
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
+      long long tw_tempty = 0, tw_full = 0, t_issue = 0;
+      const long long t_mma0 = TG_T0();
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
-        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
+        {
+          const long long t0 = TG_T0();
+          mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
+          TG_ACC(tw_tempty, t0);
+        }
         tc_fence_after();
         const uint32_t d_base = tmem_base + buf * acc_stride;
         if (HALO) {
           for (int c = 0; c < p.chunks; ++c) {
-            mbar_wait(bar_full + 8 * stage, phase, 5);
+            {
+              const long long t0 = TG_T0();
+              mbar_wait(bar_full + 8 * stage, phase, 5);
+              TG_ACC(tw_full, t0);
+            }
             tc_fence_after();
             const uint32_t sa16 = ((smem_stage0 + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
+            const long long t_i0 = TG_T0();
             if (elect_one_sync()) {
 #pragma unroll
             for (int g = 0; g < 9; ++g) {
@@ -359,6 +387,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             umma_commit(bar_empty + 8 * stage);
             }
             __syncwarp();
+            TG_ACC(t_issue, t_i0);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
         } else {
@@ -368,7 +397,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
             const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
             for (int c = 0; c < p.chunks; ++c) {
-              mbar_wait(bar_full + 8 * stage, phase, 6);
+              {
+                const long long t0 = TG_T0();
+                mbar_wait(bar_full + 8 * stage, phase, 6);
+                TG_ACC(tw_full, t0);
+              }
               tc_fence_after();
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
               const uint32_t a16 = (sa & 0x3FFFFu) >> 4;
@@ -389,6 +422,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         if (elect_one_sync()) umma_commit(bar_tfull + 8 * buf);
         __syncwarp();
       }
+      if (timing && lane == 0) {
+        unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
+        o[T_MMA_WAIT_TEMPTY] = tw_tempty; o[T_MMA_WAIT_FULL] = tw_full; o[T_MMA_ISSUE] = t_issue;
+        o[T_MMA_TOTAL] = clock64() - t_mma0; o[T_TILES] = it;
+      }
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
@@ -403,35 +441,44 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     const int chunks_out = p.bn / 64;
     const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
     int it = 0;
+    long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
+    const long long t_epi0 = TG_T0();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
       const int py = tc.y0 + ty, px = tc.x0 + tx;
       const bool inb = py < d.h && px < d.w;
+      long long t_s = TG_T0();
       if (d.epilogue == TG_EPI_NHWC_F16) {
         if (ew == 0 && lane == 0) bulk_wait_read0();   // staging of the previous tile drained
         named_bar_sync(1, 256);
       }
+      TG_ACC(te_store_wait, t_s);
       if (active) {
+        // residual (conv3x3 only, bn == 64 -> this warp's 32 columns): issue the global loads
+        // BEFORE waiting for the accumulator so their latency hides behind the MMAs of this tile
+        uint4 res[4];
+        const bool has_res = (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
+        if (has_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(
+              reinterpret_cast<const __half*>(d.residual) +
+              (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn + half * cols_per_half);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
+        }
+        t_s = TG_T0();
         mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+        TG_ACC(te_tfull, t_s);
+        t_s = TG_T0();
         tc_fence_after();
         if (d.epilogue == TG_EPI_NHWC_F16) {
-          const int pieces = cols_per_half / 32;
+          const int pieces = cols_per_half / 32;      // 1: bn <= 64 in every supported configuration
           for (int acc = 0; acc < p.n_acc; ++acc) {
             for (int pc = 0; pc < pieces; ++pc) {
               const int col0 = half * cols_per_half + pc * 32;
               uint32_t v[32];
               tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + col0 + ((uint32_t)(q * 32) << 16), v);
-              uint4 res[4];
-              const bool has_res = (d.residual != nullptr) && inb;
-              if (has_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(
-                    reinterpret_cast<const __half*>(d.residual) +
-                    (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn + col0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
-              }
               tmem_ld_wait();
               if (acc == p.n_acc - 1 && pc == pieces - 1) {
                 // all TMEM reads of this warp for this buffer are done -> hand it back to the MMA
@@ -478,6 +525,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
           }
         }
       }
+      TG_ACC(te_compute, t_s);
+      t_s = TG_T0();
       if (d.epilogue == TG_EPI_NHWC_F16) {
         fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA store
         named_bar_sync(1, 256);
@@ -489,6 +538,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
           bulk_commit();
         }
       }
+      TG_ACC(te_store, t_s);
+    }
+    if (timing && ew == 0 && lane == 0) {
+      unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
+      o[T_EPI_WAIT_STORE] = te_store_wait; o[T_EPI_WAIT_TFULL] = te_tfull; o[T_EPI_COMPUTE] = te_compute;
+      o[T_EPI_STORE] = te_store; o[T_EPI_TOTAL] = clock64() - t_epi0;
     }
     if (d.epilogue == TG_EPI_NHWC_F16 && ew == 0 && lane == 0) bulk_wait0();
   }
@@ -498,6 +553,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (timing && threadIdx.x == 0) p.dbg[blockIdx.x * T_SLOTS + T_KERNEL] = clock64() - t_kernel0;
 }
 
 // ------------------------------------------------------------------ host side
@@ -539,7 +595,14 @@ int encode_nhwc(CUtensorMap* m, const void* ptr, int c, int w, int h, int n, siz
 
 }  // namespace
 
+static unsigned long long* g_conv_timers = nullptr;
+
 extern "C" {
+
+int tg_debug_set_conv_timers(void* device_buffer) {
+  g_conv_timers = reinterpret_cast<unsigned long long*>(device_buffer);
+  return TG_OK;
+}
 
 int tg_conv_validate(const tg_conv_desc* d, const char* who) {
   TG_REQUIRE(d != nullptr, TG_E_INVALID, "%s: null descriptor", who);
@@ -574,6 +637,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
 
   KParams p;
   p.d = *d;
+  p.dbg = g_conv_timers;
   p.tiles_x = tg_ceil_div(d->w, TW);
   p.tiles_y = tg_ceil_div(d->h, TH);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Per-role cycle breakdown of conv_tcgen05_kernel (GPU only; debugging / profiling aid).
+
+Registers a device buffer with tg_debug_set_conv_timers, runs one layer configuration and prints
+the average over CTAs of every timer, per tile.  Usage:  python tools/conv_timers.py
+"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tecogan_b200 as T   # noqa: E402
+
+ops = sys.modules['tecogan-pytorch_b200.ops']
+L = sys.modules['tecogan-pytorch_b200.lib']
+NAMES = ['prod_wait_empty', 'mma_wait_tempty', 'mma_wait_full', 'mma_issue', 'mma_total', 'epi_wait_store',
+         'epi_wait_tfull', 'epi_compute', 'epi_store', 'epi_total', 'kernel', 'prologue', 'tiles']
+
+
+def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16, residual=False, a_mode=None):
+    dev = 'cuda:0'
+    wshape = (cout_real, cin, 3, 3) if kind == L.CONV_3X3 else (cin, cout_real, 3, 3)
+    pc = ops.PackedConv(torch.randn(*wshape, device=dev) * 0.05, torch.zeros(cout_real, device=dev), kind,
+                        L.ACT_RELU if epilogue == L.EPI_NHWC_F16 else L.ACT_NONE, epilogue)
+    x = torch.randn(n, h, w, cin, device=dev).half()
+    res = torch.randn(n, h, w, pc.cout, device=dev).half() if residual else None
+    y = None
+    if epilogue == L.EPI_OUT_NCHW_F32:
+        y = torch.zeros(n, cout_real, h, w, device=dev)
+    for _ in range(3):
+        y = pc(x, y=y, residual=res, a_mode=a_mode)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    lib = L.load()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    pc(x, y=y, residual=res, a_mode=a_mode)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
+    t = buf.view(148, 16).cpu().double()
+    active = t[:, 10] > 0
+    t = t[active]
+    tiles = t[:, 12].mean().item()
+    out = {'layer': name, 'us': e0.elapsed_time(e1) * 1e3, 'ctas': int(active.sum()), 'tiles_per_cta': tiles}
+    for i, nm in enumerate(NAMES[:-1]):
+        out[nm] = round(t[:, i].mean().item())
+    out['per_tile'] = {nm: round(out[nm] / max(tiles, 1)) for nm in NAMES[:10]}
+    print(json.dumps(out))
+    return out
+
+
+if __name__ == '__main__':
+    run('res 64->64 halo n4', 64, 64, 134, 320, 4)
+    run('res 64->64 halo+residual n4', 64, 64, 134, 320, 4, residual=True)
+    run('res 64->64 tap n4', 64, 64, 134, 320, 4, a_mode=L.AMODE_TAP)
+    run('convT 64->64 268x640 n4', 64, 64, 268, 640, 4, kind=L.CONVT_3X3_S2)
+    run('conv_out 64->3 536x1280 n4', 64, 3, 536, 1280, 4, epilogue=L.EPI_OUT_NCHW_F32)
+    run('fnet 256->256 16x40 n4', 256, 256, 16, 40, 4)

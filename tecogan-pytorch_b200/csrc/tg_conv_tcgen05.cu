@@ -251,7 +251,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 48);
   float* bias_s = reinterpret_cast<float*>(sm + 1024);
 
-  const int epi_warps_active = (p.bn >= 64) ? 8 : 4;
+  const int epi_warps_active = 4;   // the 4 warps of the epilogue group that owns the buffer
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -331,14 +331,19 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       if (timing) p.dbg[blockIdx.x * T_SLOTS + T_PROD_WAIT_EMPTY] = tw;
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    // The whole warp walks the (warp-uniform) pipeline; one elected lane issues the MMAs.
+  } else if (warp == 1 || warp == 3) {
+    // ============================================================ MMA issuers
+    // Two issuer warps: warp 1 owns accumulator buffer 0 (even tiles of this CTA), warp 3 owns
+    // buffer 1 (odd tiles).  While one warp's MMAs occupy the tensor pipe the other is already
+    // polling the barriers of the next tile, so the fixed mbarrier / commit latencies between
+    // tiles are hidden.  Each warp walks its (warp-uniform) pipeline; one elected lane issues.
     {
+      const int mw = warp == 1 ? 0 : 1;
+      const int spt = (HALO ? 1 : 9) * p.chunks;      // smem stages consumed per tile
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
+      int it = mw;
       const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
       // descriptor templates: everything but the 14-bit start address is constant per kernel
       constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
@@ -349,9 +354,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       long long tw_tempty = 0, tw_full = 0, t_issue = 0;
       const long long t_mma0 = TG_T0();
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+        const int buf = mw;
         const uint32_t bphase = (it >> 1) & 1;
+        {
+          const int gs = it * spt;                    // stages are filled in tile order
+          stage = gs % p.n_stages;
+          phase = (uint32_t)(gs / p.n_stages) & 1u;
+        }
         {
           const long long t0 = TG_T0();
           mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
@@ -422,7 +432,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         if (elect_one_sync()) umma_commit(bar_tfull + 8 * buf);
         __syncwarp();
       }
-      if (timing && lane == 0) {
+      if (timing && lane == 0 && mw == 0) {
         unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
         o[T_MMA_WAIT_TEMPTY] = tw_tempty; o[T_MMA_WAIT_FULL] = tw_full; o[T_MMA_ISSUE] = t_issue;
         o[T_MMA_TOTAL] = clock64() - t_mma0; o[T_TILES] = it;
@@ -430,122 +440,126 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    const int ew = warp - 4;
+    // Two groups of 4 warps; group g owns TMEM accumulator buffer g and therefore every second
+    // tile of this CTA, so one group's TMEM->regs->smem->TMA-store chain overlaps the other
+    // group's and both overlap the MMAs.  Warp q of a group reads TMEM lanes [32q, 32q+32) =
+    // tile rows, all bn columns.  Each group has two 16 KB staging buffers (ring): the TMA store
+    // of one (accumulator, 64-channel chunk) unit drains while the next unit is being written.
+    const int group = (warp - 4) >> 2;
+    const int gtid = threadIdx.x - 128 - group * 128;   // 0..127 inside the group
     const int q = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = ew >> 2;      // column half
-    const bool active = (p.bn >= 64) || half == 0;
-    const int cols_per_half = (p.bn >= 64) ? p.bn / 2 : p.bn;
     const int r = q * 32 + lane;   // row of the tile = TMEM lane
     const int ty = r >> 3, tx = r & 7;
     const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
-    const int chunks_out = p.bn / 64;
     const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
-    int it = 0;
+    const uint32_t stg_base = p.off_staging + (uint32_t)group * 2u * 16384u;
+    uint32_t unit = 0;             // staging ring position of this group
+    const int buf = group;
     long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
     const long long t_epi0 = TG_T0();
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+    int it = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
       const uint32_t bphase = (it >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
       const int py = tc.y0 + ty, px = tc.x0 + tx;
       const bool inb = py < d.h && px < d.w;
       long long t_s = TG_T0();
-      if (d.epilogue == TG_EPI_NHWC_F16) {
-        if (ew == 0 && lane == 0) bulk_wait_read0();   // staging of the previous tile drained
-        named_bar_sync(1, 256);
+      // operands that come from global memory are fetched BEFORE waiting for the accumulator so
+      // their latency hides behind the MMAs of this tile
+      uint4 res[8];
+      float yprev[4];
+      const bool has_res = (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __half*>(d.residual) +
+            (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res[i] = __ldg(rp + i);
       }
-      TG_ACC(te_store_wait, t_s);
-      if (active) {
-        // residual (conv3x3 only, bn == 64 -> this warp's 32 columns): issue the global loads
-        // BEFORE waiting for the accumulator so their latency hides behind the MMAs of this tile
-        uint4 res[4];
-        const bool has_res = (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
-        if (has_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(
-              reinterpret_cast<const __half*>(d.residual) +
-              (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn + half * cols_per_half);
+      if (d.epilogue == TG_EPI_OUT_NCHW_F32 && inb) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) res[i] = __ldg(rp + i);
-        }
-        t_s = TG_T0();
-        mbar_wait(bar_tfull + 8 * buf, bphase, 7);
-        TG_ACC(te_tfull, t_s);
-        t_s = TG_T0();
-        tc_fence_after();
-        if (d.epilogue == TG_EPI_NHWC_F16) {
-          const int pieces = cols_per_half / 32;      // 1: bn <= 64 in every supported configuration
-          for (int acc = 0; acc < p.n_acc; ++acc) {
-            for (int pc = 0; pc < pieces; ++pc) {
-              const int col0 = half * cols_per_half + pc * 32;
-              uint32_t v[32];
-              tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + col0 + ((uint32_t)(q * 32) << 16), v);
-              tmem_ld_wait();
-              if (acc == p.n_acc - 1 && pc == pieces - 1) {
-                // all TMEM reads of this warp for this buffer are done -> hand it back to the MMA
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-              }
-              uint8_t* srow = sm + p.off_staging + (size_t)(acc * chunks_out + (col0 >> 6)) * 16384 + r * 128;
-              const int cbase = (col0 & 63) >> 3;   // first 16-byte chunk inside the 128-byte row
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                __align__(16) __half2 o[4];
-                const __half2* rh = reinterpret_cast<const __half2*>(&res[i]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int cidx = i * 8 + j * 2;
-                  float a0 = tg_epi_val(__uint_as_float(v[cidx]), bias_s[tc.nb * p.bn + col0 + cidx], d.act);
-                  float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bias_s[tc.nb * p.bn + col0 + cidx + 1], d.act);
-                  if (has_res) {
-                    const float2 rf = __half22float2(rh[j]);
-                    a0 += rf.x; a1 += rf.y;
-                  }
-                  o[j] = __floats2half2_rn(a0, a1);
-                }
-                *reinterpret_cast<uint4*>(srow + (((cbase + i) ^ (r & 7)) << 4)) =
-                    *reinterpret_cast<const uint4*>(o);
-              }
-            }
-          }
-        } else {
-          // NCHW fp32 epilogues: cout == 16, only the first cout_real columns are real
-          uint32_t v[16];
-          tmem_ld16(tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16), v);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-          if (inb) {
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-              if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
-              else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
-            }
-          }
-        }
+        for (int ch = 0; ch < 4; ++ch)
+          if (ch < d.cout_real)
+            yprev[ch] = reinterpret_cast<const float*>(d.y)[(((size_t)tc.n * d.cout_real + ch) * d.h + py) * d.w + px];
       }
-      TG_ACC(te_compute, t_s);
+      mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+      TG_ACC(te_tfull, t_s);
       t_s = TG_T0();
+      tc_fence_after();
       if (d.epilogue == TG_EPI_NHWC_F16) {
-        fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA store
-        named_bar_sync(1, 256);
-        if (ew == 0 && lane == 0) {
-          for (int acc = 0; acc < p.n_acc; ++acc)
-            for (int cc = 0; cc < chunks_out; ++cc)
-              tma_store_4d(ymaps[acc], base + p.off_staging + (uint32_t)(acc * chunks_out + cc) * 16384u,
-                           tc.nb * p.bn + cc * 64, tc.x0, tc.y0, tc.n);
-          bulk_commit();
+        for (int acc = 0; acc < p.n_acc; ++acc, ++unit) {
+          uint8_t* srow = sm + stg_base + (unit & 1u) * 16384u + r * 128;
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {                // bn == 64: two 32-column pieces
+            uint32_t v[32];
+            tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + pc * 32 + ((uint32_t)(q * 32) << 16), v);
+            tmem_ld_wait();
+            if (acc == p.n_acc - 1 && pc == 1) {
+              // all TMEM reads of this warp for this buffer are done -> hand it back to the MMA
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            }
+            const float4* bias4 = reinterpret_cast<const float4*>(bias_s + tc.nb * p.bn + pc * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __align__(16) __half2 o[4];
+              const __half2* rh = reinterpret_cast<const __half2*>(&res[pc * 4 + i]);
+              const float4 b0 = bias4[i * 2], b1 = bias4[i * 2 + 1];
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cidx = i * 8 + j * 2;
+                float a0 = tg_epi_val(__uint_as_float(v[cidx]), bb[j * 2], d.act);
+                float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bb[j * 2 + 1], d.act);
+                if (has_res) {
+                  const float2 rf = __half22float2(rh[j]);
+                  a0 += rf.x; a1 += rf.y;
+                }
+                o[j] = __floats2half2_rn(a0, a1);
+              }
+              *reinterpret_cast<uint4*>(srow + (((pc * 4 + i) ^ (r & 7)) << 4)) =
+                  *reinterpret_cast<const uint4*>(o);
+            }
+          }
+          TG_ACC(te_compute, t_s);
+          t_s = TG_T0();
+          // the store issued one unit ago must have finished reading its buffer before the
+          // NEXT unit overwrites it; the barrier below publishes that to the whole group
+          if (gtid == 0) bulk_wait_read0();
+          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA store
+          named_bar_sync(1 + group, 128);
+          if (gtid == 0) {
+            tma_store_4d(ymaps[acc], base + stg_base + (unit & 1u) * 16384u, tc.nb * p.bn, tc.x0, tc.y0, tc.n);
+            bulk_commit();
+          }
+          TG_ACC(te_store, t_s);
+          t_s = TG_T0();
         }
+      } else {
+        // NCHW fp32 epilogues: bn == 16, only the first cout_real columns are real
+        uint32_t v[16];
+        tmem_ld16(tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16), v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (inb) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
+            else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]), yprev[ch]);
+          }
+        }
+        TG_ACC(te_compute, t_s);
       }
-      TG_ACC(te_store, t_s);
     }
-    if (timing && ew == 0 && lane == 0) {
+    if (timing && gtid == 0 && group == 0) {
       unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
       o[T_EPI_WAIT_STORE] = te_store_wait; o[T_EPI_WAIT_TFULL] = te_tfull; o[T_EPI_COMPUTE] = te_compute;
       o[T_EPI_STORE] = te_store; o[T_EPI_TOTAL] = clock64() - t_epi0;
     }
-    if (d.epilogue == TG_EPI_NHWC_F16 && ew == 0 && lane == 0) bulk_wait0();
+    if (d.epilogue == TG_EPI_NHWC_F16 && gtid == 0) bulk_wait0();
   }
 
   // ------------------------------------------------------------ teardown
@@ -646,7 +660,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
 
   const uint32_t b_total = 9u * p.chunks * p.b_tile_bytes;
-  uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? (uint32_t)p.n_acc * (d->cout / 64) * 16384u : 0u;
+  uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? 4u * 16384u : 0u;   // 2 groups x 2-deep ring
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
@@ -670,10 +684,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_stage_bytes = (uint32_t)p.bn * 128u;
   p.num_tiles *= p.n_split;
   p.idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  if (d->epilogue == TG_EPI_NHWC_F16) {
-    staging = (uint32_t)p.n_acc * (p.bn / 64) * 16384u;
-    fixed = 1024u + kHeaderBytes + staging;
-  }
+  TG_REQUIRE(p.bn == 64 || p.bn == 16, TG_E_UNSUPPORTED, "conv_tcgen05: per-CTA N must be 64 (or 16)");
   if (p.halo) {
     p.box_w = hbox_w; p.box_h = hbox_h;
     p.org_x = d->kind == TG_CONV_3X3 ? -1 : 0;

@@ -15,11 +15,16 @@ __device__ __forceinline__ void tg_epi_flow(const tg_conv_desc& d, int n, int y,
 // y already holds upsample_func(lr_curr) (tg_upsample_nchw_f32); fp32 add is commutative, so
 // (conv + bias) + up is the reference's value.
 __device__ __forceinline__ void tg_epi_out(const tg_conv_desc& d, int n, int y, int x, int H,
-                                           int W, int ch, float acc) {
-  if (ch < d.cout_real) {
-    float* o = reinterpret_cast<float*>(d.y) + (((size_t)n * d.cout_real + ch) * H + y) * W + x;
-    *o = (acc + __ldg(d.bias + ch)) + *o;
-  }
+                                           int W, int ch, float acc, float y_prev) {
+  if (ch < d.cout_real)
+    reinterpret_cast<float*>(d.y)[(((size_t)n * d.cout_real + ch) * H + y) * W + x] =
+        (acc + __ldg(d.bias + ch)) + y_prev;
+}
+__device__ __forceinline__ float tg_epi_out_prev(const tg_conv_desc& d, int n, int y, int x, int H,
+                                                 int W, int ch) {
+  return ch < d.cout_real
+             ? reinterpret_cast<const float*>(d.y)[(((size_t)n * d.cout_real + ch) * H + y) * W + x]
+             : 0.f;
 }
 
 // TG_EPI_NHWC_F16 value: act(acc + bias) [+ residual]
@@ -48,6 +53,7 @@ __device__ __forceinline__ void tg_epilogue_store8(const tg_conv_desc& d, int n,
     for (int j = 0; j < 8; ++j) tg_epi_flow(d, n, oy, ox, OH, OW, c0 + j, a[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) tg_epi_out(d, n, oy, ox, OH, OW, c0 + j, a[j]);
+    for (int j = 0; j < 8; ++j)
+      tg_epi_out(d, n, oy, ox, OH, OW, c0 + j, a[j], tg_epi_out_prev(d, n, oy, ox, OH, OW, c0 + j));
   }
 }

@@ -86,8 +86,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 3000000000LL) {
-      printf("tg_conv_tcgen05: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
-             blockIdx.x, threadIdx.x, parity);
+      if ((threadIdx.x & 31) == 0 && blockIdx.x < 2)
+        printf("tg_conv_tcgen05: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+               blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }
@@ -333,12 +334,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp == 1 || warp == 3) {
     // ============================================================ MMA issuers
-    // Two issuer warps: warp 1 owns accumulator buffer 0 (even tiles of this CTA), warp 3 owns
-    // buffer 1 (odd tiles).  While one warp's MMAs occupy the tensor pipe the other is already
-    // polling the barriers of the next tile, so the fixed mbarrier / commit latencies between
-    // tiles are hidden.  Each warp walks its (warp-uniform) pipeline; one elected lane issues.
-    {
-      const int mw = warp == 1 ? 0 : 1;
+    // HALO mode (one smem stage per tile): two issuer warps -- warp 1 owns accumulator buffer 0
+    // (even tiles of this CTA), warp 3 buffer 1 (odd tiles).  While one warp's MMAs occupy the
+    // tensor pipe the other is already polling the barriers of the next tile, so the fixed
+    // mbarrier / commit latencies between tiles are hidden.  A parity wait is only sound when the
+    // waiter is at most one phase ahead of the barrier; with one stage per tile the TMEM
+    // hand-shake (tile i+2 cannot start before the epilogue of tile i) guarantees that.  In the
+    // per-tap modes a tile spans more stages than the ring, so warp 1 alone issues every tile.
+    // Each warp walks its (warp-uniform) pipeline; one elected lane issues.
+    const bool dual = HALO && p.chunks == 1;
+    if (dual || warp == 1) {
+      const int mw = (dual && warp == 3) ? 1 : 0;
+      const int tstep = dual ? 2 : 1;
       const int spt = (HALO ? 1 : 9) * p.chunks;      // smem stages consumed per tile
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
@@ -354,8 +361,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       long long tw_tempty = 0, tw_full = 0, t_issue = 0;
       const long long t_mma0 = TG_T0();
-      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
-        const int buf = mw;
+      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.num_tiles; tile += tstep * gridDim.x, it += tstep) {
+        const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         {
           const int gs = it * spt;                    // stages are filled in tile order

@@ -31,6 +31,7 @@ extern "C" {
 #endif
 
 #define TG_ABI_VERSION 1
+#define TG_TAPN_ROWS 48   /* 9 taps x 4 output channels, padded to a multiple of 16 */
 
 enum {
   TG_OK = 0,
@@ -68,6 +69,13 @@ int tg_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, void* packed
  * (tecogan_nets.py:119-126) -> 9 tiles grouped by output parity (1/2/2/4 taps) */
 int tg_pack_convT3x3s2_weights(const float* w_iohw, int cin, int cout, void* packed,
                                int cout_pad, int cin_pad, void* stream);
+/* Thin heads (cout <= 4: FNet flow head 32->2, SRNet conv_out 64->3) use the "tap-major N"
+ * layout: one tile per 64-ch chunk, [48 rows][64 k], row = tap*4 + co (rows >= 36 zero).  One
+ * MMA group then yields all nine tap products of a pixel (N = 48) and the 3x3 shift-add happens
+ * in the epilogue -- 4 MMAs per 128 pixels instead of 36.  Used with the two NCHW epilogues. */
+size_t tg_packed_weight_bytes_tapn(int cin_pad);
+int tg_pack_conv3x3_weights_tapn(const float* w_oihw, int cout, int cin, void* packed, int cin_pad,
+                                 void* stream);
 
 /* ------------------------------------------------------------------------
  * 3x3 convolution / stride-2 transposed convolution as tcgen05 implicit GEMM.
@@ -84,7 +92,8 @@ typedef struct tg_conv_desc {
   void* y;              /* see epilogue; convT writes [n,2h,2w,cout]                     */
   int32_t n, h, w;      /* input batch / height / width                                  */
   int32_t cin, cout;    /* stored channel counts: cin in {64,128,256}; cout in {64,128,256}
-                           for TG_EPI_NHWC_F16, 16 for the two NCHW epilogues            */
+                           for TG_EPI_NHWC_F16, 48 (= TG_TAPN_ROWS, tap-major N packing)
+                           for the two NCHW epilogues                                    */
   int32_t cout_real;    /* NCHW epilogues: channels actually written (2 resp. 3)         */
   int32_t kind;         /* TG_CONV_3X3 | TG_CONVT_3X3_S2                                 */
   int32_t act;          /* TG_ACT_*                                                      */

@@ -35,11 +35,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
   }
 }
 
+// tap-major N layout for thin heads: tile per chunk [48 rows][64 k], row = tap*4 + co
+__global__ void pack_weights_tapn_kernel(const float* __restrict__ w, __half* __restrict__ packed,
+                                         int cout, int cin, int cin_pad) {
+  const int chunks = cin_pad / 64;
+  const size_t total = (size_t)chunks * TG_TAPN_ROWS * 64;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % 64);
+    const int row = (int)((i / 64) % TG_TAPN_ROWS);
+    const int chunk = (int)(i / ((size_t)64 * TG_TAPN_ROWS));
+    const int tap = row >> 2, co = row & 3, ci = chunk * 64 + k;
+    float v = 0.f;
+    if (tap < 9 && co < cout && ci < cin) v = w[(((size_t)co * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
+    unsigned char* base = reinterpret_cast<unsigned char*>(packed) + (size_t)chunk * TG_TAPN_ROWS * 128;
+    *reinterpret_cast<__half*>(base + tg_wtile_off(row, k)) = __float2half(v);
+  }
+}
+
 // ------------------------------------------------------------------ cross-check conv
 __global__ void conv_simt_kernel(tg_conv_desc d) {
   const int chunks = d.cin / 64;
   const int n_acc = d.kind == TG_CONV_3X3 ? 1 : 4;
-  const int co_groups = d.cout / 8;
+  const bool tapn = d.epilogue != TG_EPI_NHWC_F16;
+  const int co_groups = tapn ? 1 : d.cout / 8;
   const size_t total = (size_t)d.n * d.h * d.w * n_acc * co_groups;
   const __half* x = reinterpret_cast<const __half*>(d.x);
   const unsigned char* wp = reinterpret_cast<const unsigned char*>(d.weights);
@@ -62,11 +81,19 @@ __global__ void conv_simt_kernel(tg_conv_desc d) {
       const __half* px = x + (((size_t)nn * d.h + iy) * d.w + ix) * d.cin;
       for (int ci = 0; ci < d.cin; ++ci) {
         const float xv = __half2float(px[ci]);
-        const unsigned char* tile = wp + (size_t)(g * chunks + ci / 64) * d.cout * 128;
+        if (tapn) {   // NCHW heads: tile per chunk, row = tap*4 + co, 4 real output channels max
+          const unsigned char* tile = wp + (size_t)(ci / 64) * TG_TAPN_ROWS * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          a[j] += xv * __half2float(*reinterpret_cast<const __half*>(
-                           tile + tg_wtile_off(cg * 8 + j, ci & 63)));
+          for (int j = 0; j < 4; ++j)
+            a[j] += xv * __half2float(*reinterpret_cast<const __half*>(
+                             tile + tg_wtile_off(g * 4 + j, ci & 63)));
+        } else {
+          const unsigned char* tile = wp + (size_t)(g * chunks + ci / 64) * d.cout * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            a[j] += xv * __half2float(*reinterpret_cast<const __half*>(
+                             tile + tg_wtile_off(cg * 8 + j, ci & 63)));
+        }
       }
     }
     // output pixel of this accumulator
@@ -111,13 +138,30 @@ int tg_pack_convT3x3s2_weights(const float* w_iohw, int cin, int cout, void* pac
   return pack_common(w_iohw, TG_CONVT_3X3_S2, cout, cin, packed, cout_pad, cin_pad, stream);
 }
 
+size_t tg_packed_weight_bytes_tapn(int cin_pad) {
+  if (cin_pad <= 0 || cin_pad % 64 != 0) return 0;
+  return (size_t)(cin_pad / 64) * TG_TAPN_ROWS * 128;
+}
+
+int tg_pack_conv3x3_weights_tapn(const float* w_oihw, int cout, int cin, void* packed, int cin_pad,
+                                 void* stream) {
+  TG_REQUIRE(w_oihw && packed, TG_E_INVALID, "pack_weights_tapn: null pointer");
+  TG_REQUIRE(cout >= 1 && cout <= 4 && cin > 0 && cin <= cin_pad && cin_pad % 64 == 0, TG_E_UNSUPPORTED,
+             "pack_weights_tapn: cout=%d (<=4) cin=%d cin_pad=%d", cout, cin, cin_pad);
+  pack_weights_tapn_kernel<<<(cin_pad / 64) * 12, 256, 0, (cudaStream_t)stream>>>(
+      w_oihw, (__half*)packed, cout, cin, cin_pad);
+  TG_CUDA_LAUNCH_CHECK("pack_weights_tapn");
+  return TG_OK;
+}
+
 int tg_conv_validate(const tg_conv_desc* d, const char* who);
 
 int tg_conv_simt(const tg_conv_desc* d, void* stream) {
   int rc = tg_conv_validate(d, "conv_simt");
   if (rc != TG_OK) return rc;
   const int n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
-  const size_t total = (size_t)d->n * d->h * d->w * n_acc * (d->cout / 8);
+  const size_t total = (size_t)d->n * d->h * d->w * n_acc *
+                       (d->epilogue != TG_EPI_NHWC_F16 ? 1 : d->cout / 8);
   size_t grid = (total + 127) / 128;
   if (grid > 148 * 64) grid = 148 * 64;
   conv_simt_kernel<<<(int)grid, 128, 0, (cudaStream_t)stream>>>(*d);

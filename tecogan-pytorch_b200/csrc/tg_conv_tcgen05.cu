@@ -35,6 +35,13 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kHeaderBytes = 2048;   // barriers + tmem ptr (first 1 KB) + bias (second 1 KB)
 constexpr uint32_t kTapABytes = TH * TW * 128;  // 16 KB
 constexpr uint32_t kSmemLimit = 232448;   // 227 KB opt-in limit per CTA
+// A-operand modes (template parameter MODE)
+constexpr int MODE_TAP = 0;    // one 16x8 box per (tap, chunk)
+constexpr int MODE_HALO = 1;   // one 18x10 halo box per (tile, chunk), taps = descriptor shifts
+constexpr int MODE_TAPN = 2;   // thin heads: one 16x8 box per (tile, chunk), N = 9 taps x 4 couts,
+                               // 3x3 shift-add in the epilogue; tiles overlap by one pixel ring
+constexpr int kTapnStepY = TH - 2, kTapnStepX = TW - 2;   // 14 x 6 valid outputs per TAPN tile
+constexpr uint32_t kTapnEBytes = 128 * 9 * 16;            // exchange buffer: [128 px][9 taps] float4
 
 struct KParams {
   tg_conv_desc d;
@@ -42,6 +49,8 @@ struct KParams {
   int chunks, n_acc;
   int halo, b_resident;
   int box_w, box_h, org_x, org_y;
+  int step_y, step_x;              // output pixels a tile advances by (16x8; 14x6 for MODE_TAPN)
+  uint32_t acc_stride;             // TMEM columns per accumulator buffer
   int n_stages;
   int n_split, bn;                 // output channels are split over n_split CTAs of bn columns
   uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
@@ -220,13 +229,13 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
   t.nb = tile - sp * p.n_split;
   t.n = sp / per_img;
   const int r = sp - t.n * per_img;
-  t.y0 = (r / p.tiles_x) * TH;
-  t.x0 = (r % p.tiles_x) * TW;
+  t.y0 = (r / p.tiles_x) * p.step_y;
+  t.x0 = (r % p.tiles_x) * p.step_x;
   return t;
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int KIND, bool HALO>
+template <int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                     const __grid_constant__ CUtensorMap map_y0,
@@ -284,7 +293,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   const uint32_t smem_b = base + p.off_b;
   const uint32_t smem_stage0 = base + p.off_stage;
   const unsigned char* wglob = reinterpret_cast<const unsigned char*>(d.weights);
-  const int n_tiles_w = 9 * p.chunks;
+  const int n_tiles_w = (MODE == MODE_TAPN ? 1 : 9) * p.chunks;
 
   if (warp == 0) {
     // ============================================================ TMA producer
@@ -299,7 +308,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       long long tw = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
-        if (HALO) {
+        if (MODE != MODE_TAP) {
           for (int c = 0; c < p.chunks; ++c) {
             const long long t0 = TG_T0();
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
@@ -342,20 +351,20 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     // hand-shake (tile i+2 cannot start before the epilogue of tile i) guarantees that.  In the
     // per-tap modes a tile spans more stages than the ring, so warp 1 alone issues every tile.
     // Each warp walks its (warp-uniform) pipeline; one elected lane issues.
-    const bool dual = HALO && p.chunks == 1;
+    const bool dual = MODE != MODE_TAP && p.chunks == 1;
     if (dual || warp == 1) {
       const int mw = (dual && warp == 3) ? 1 : 0;
       const int tstep = dual ? 2 : 1;
-      const int spt = (HALO ? 1 : 9) * p.chunks;      // smem stages consumed per tile
+      const int spt = (MODE != MODE_TAP ? 1 : 9) * p.chunks;      // smem stages consumed per tile
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
       uint32_t phase = 0;
       int it = mw;
-      const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
+      const uint32_t acc_stride = p.acc_stride;
       // descriptor templates: everything but the 14-bit start address is constant per kernel
       constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
       constexpr int kOrg = (KIND == TG_CONV_3X3) ? -1 : 0;
-      const uint64_t a_hi = make_sdesc(0, HALO ? (uint32_t)kBoxW * 128u : 1024u);
+      const uint64_t a_hi = make_sdesc(0, MODE == MODE_HALO ? (uint32_t)kBoxW * 128u : 1024u);
       const uint64_t b_hi = make_sdesc(0, 1024u);
       const uint32_t btb16 = p.b_tile_bytes >> 4;
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
@@ -376,7 +385,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         tc_fence_after();
         const uint32_t d_base = tmem_base + buf * acc_stride;
-        if (HALO) {
+        if (MODE != MODE_TAP) {
+          constexpr int NG = MODE == MODE_TAPN ? 1 : 9;   // TAPN: one group, all taps live in N
           for (int c = 0; c < p.chunks; ++c) {
             {
               const long long t0 = TG_T0();
@@ -388,12 +398,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
             const long long t_i0 = TG_T0();
             if (elect_one_sync()) {
 #pragma unroll
-            for (int g = 0; g < 9; ++g) {
-              constexpr int kUnused = 0; (void)kUnused;
-              const TgGroup gr = tg_group(KIND, g);
+            for (int g = 0; g < NG; ++g) {
+              const TgGroup gr = MODE == MODE_TAPN ? TgGroup{0, 0, 0, 0, 0} : tg_group(KIND, g);
               // first MMA into an accumulator (per tile) overwrites, the rest accumulate
               const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
-              const uint32_t a16 = sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
+              const uint32_t a16 = MODE == MODE_TAPN
+                                       ? sa16
+                                       : sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
               const uint32_t b16 = smem_b16 + (uint32_t)(g * p.chunks + c) * btb16;
               const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
 #pragma unroll
@@ -457,7 +468,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;   // row of the tile = TMEM lane
     const int ty = r >> 3, tx = r & 7;
-    const uint32_t acc_stride = (uint32_t)(p.n_acc * p.bn);
+    const uint32_t acc_stride = p.acc_stride;
     const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
     const uint32_t stg_base = p.off_staging + (uint32_t)group * 2u * 16384u;
     uint32_t unit = 0;             // staging ring position of this group
@@ -468,8 +479,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
       const uint32_t bphase = (it >> 1) & 1;
       const TileCoord tc = tile_coord(p, tile);
-      const int py = tc.y0 + ty, px = tc.x0 + tx;
-      const bool inb = py < d.h && px < d.w;
+      // MODE_TAPN: thread = input position (halo ring included); interior positions are outputs
+      const int py = tc.y0 + ty + (MODE == MODE_TAPN ? -1 : 0), px = tc.x0 + tx + (MODE == MODE_TAPN ? -1 : 0);
+      const bool interior = MODE != MODE_TAPN || (ty >= 1 && ty <= TH - 2 && tx >= 1 && tx <= TW - 2);
+      const bool inb = interior && py < d.h && px < d.w;
       long long t_s = TG_T0();
       // operands that come from global memory are fetched BEFORE waiting for the accumulator so
       // their latency hides behind the MMAs of this tile
@@ -544,18 +557,34 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
           t_s = TG_T0();
         }
       } else {
-        // NCHW fp32 epilogues: bn == 16, only the first cout_real columns are real
-        uint32_t v[16];
-        tmem_ld16(tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16), v);
+        // MODE_TAPN heads: D[pos][tap*4+co] = x[pos] . W[tap][co]; out[p] = sum_taps D[p+off(tap)][tap].
+        // Positions exchange their nine float4 tap products through shared memory.
+        uint32_t v[48];
+        const uint32_t tad = tmem_base + buf * acc_stride + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(tad, v);
+        tmem_ld16(tad + 32, v + 32);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it >> 1) & 1)) * kTapnEBytes);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+          E[r * 9 + tap] = make_float4(__uint_as_float(v[tap * 4]), __uint_as_float(v[tap * 4 + 1]),
+                                       __uint_as_float(v[tap * 4 + 2]), __uint_as_float(v[tap * 4 + 3]));
+        named_bar_sync(1 + group, 128);
         if (inb) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const float4 e = E[(r + (tap / 3 - 1) * TW + (tap % 3 - 1)) * 9 + tap];
+            a.x += e.x; a.y += e.y; a.z += e.z; a.w += e.w;
+          }
+          const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]));
-            else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, __uint_as_float(v[ch]), yprev[ch]);
+            if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, av[ch]);
+            else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, av[ch], yprev[ch]);
           }
         }
         TG_ACC(te_compute, t_s);
@@ -640,8 +669,8 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who) {
     TG_REQUIRE(!(d->kind == TG_CONVT_3X3_S2 && d->cout != 64), TG_E_UNSUPPORTED,
                "%s: convT needs cout == 64 (4 parity accumulators in TMEM)", who);
   } else if (d->epilogue == TG_EPI_FLOW_NCHW_F32 || d->epilogue == TG_EPI_OUT_NCHW_F32) {
-    TG_REQUIRE(d->kind == TG_CONV_3X3 && d->cout == 16 && d->cout_real >= 1 && d->cout_real <= 4,
-               TG_E_UNSUPPORTED, "%s: NCHW epilogues need conv3x3, cout=16, cout_real<=4", who);
+    TG_REQUIRE(d->kind == TG_CONV_3X3 && d->cout == TG_TAPN_ROWS && d->cout_real >= 1 && d->cout_real <= 4,
+               TG_E_UNSUPPORTED, "%s: NCHW epilogues need conv3x3, cout=48 (tap-major N), cout_real<=4", who);
     TG_REQUIRE(d->residual == nullptr, TG_E_UNSUPPORTED, "%s: residual with NCHW epilogue", who);
   } else {
     TG_REQUIRE(false, TG_E_INVALID, "%s: epilogue %d", who, d->epilogue);
@@ -659,15 +688,19 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   KParams p;
   p.d = *d;
   p.dbg = g_conv_timers;
-  p.tiles_x = tg_ceil_div(d->w, TW);
-  p.tiles_y = tg_ceil_div(d->h, TH);
+  const bool tapn = d->epilogue != TG_EPI_NHWC_F16;
+  p.step_y = tapn ? kTapnStepY : TH;
+  p.step_x = tapn ? kTapnStepX : TW;
+  p.tiles_x = tg_ceil_div(d->w, p.step_x);
+  p.tiles_y = tg_ceil_div(d->h, p.step_y);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
   p.chunks = d->cin / 64;
   p.n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
 
-  const uint32_t b_total = 9u * p.chunks * p.b_tile_bytes;
-  uint32_t staging = d->epilogue == TG_EPI_NHWC_F16 ? 4u * 16384u : 0u;   // 2 groups x 2-deep ring
+  const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_tile_bytes;
+  // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
+  uint32_t staging = tapn ? 4u * kTapnEBytes : 4u * 16384u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
@@ -679,6 +712,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // weights and split N over CTAs instead of making every CTA load all of them
   const bool can_resident_tap = d->cout <= 64 && fixed + b_total + 2u * kTapABytes <= kSmemLimit;
   int mode = d->a_mode;
+  if (tapn) mode = TG_AMODE_TAP;          // placeholder; thin heads always run MODE_TAPN below
   if (mode == TG_AMODE_AUTO) mode = can_resident_halo ? TG_AMODE_HALO : TG_AMODE_TAP;
   TG_REQUIRE(!(mode == TG_AMODE_HALO && !can_resident_halo), TG_E_UNSUPPORTED,
              "conv_tcgen05: halo mode needs the weights resident in smem (cin=%d cout=%d)", d->cin, d->cout);
@@ -691,8 +725,15 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_stage_bytes = (uint32_t)p.bn * 128u;
   p.num_tiles *= p.n_split;
   p.idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  TG_REQUIRE(p.bn == 64 || p.bn == 16, TG_E_UNSUPPORTED, "conv_tcgen05: per-CTA N must be 64 (or 16)");
-  if (p.halo) {
+  TG_REQUIRE(p.bn == 64 || (tapn && p.bn == TG_TAPN_ROWS), TG_E_UNSUPPORTED,
+             "conv_tcgen05: per-CTA N must be 64 (48 for the thin heads)");
+  TG_REQUIRE(!tapn || p.b_resident, TG_E_UNSUPPORTED, "conv_tcgen05: thin head weights must fit in smem");
+  p.acc_stride = tapn ? 64u : (uint32_t)(p.n_acc * p.bn);
+  if (tapn) {
+    p.box_w = TW; p.box_h = TH; p.org_x = -1; p.org_y = -1;
+    p.a_bytes = kTapABytes;
+    p.stage_bytes = kTapABytes;
+  } else if (p.halo) {
     p.box_w = hbox_w; p.box_h = hbox_h;
     p.org_x = d->kind == TG_CONV_3X3 ? -1 : 0;
     p.org_y = p.org_x;
@@ -720,7 +761,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   rc = encode_nhwc(&map_a, d->x, d->cin, d->w, d->h, d->n, (size_t)d->cin, (size_t)d->w * d->cin,
                    (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
   if (rc != TG_OK) return rc;
-  if (d->epilogue == TG_EPI_NHWC_F16) {
+  if (!tapn) {
     if (d->kind == TG_CONV_3X3) {
       rc = encode_nhwc(&map_y[0], d->y, d->cout, d->w, d->h, d->n, (size_t)d->cout, (size_t)d->w * d->cout,
                        (size_t)d->h * d->w * d->cout, 64, TW, TH);
@@ -748,8 +789,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
     e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)kSmemLimit);                                                     \
     if (e != cudaSuccess) attr_err = e;
-    TG_SET_ATTR(TG_CONV_3X3, true) TG_SET_ATTR(TG_CONV_3X3, false)
-    TG_SET_ATTR(TG_CONVT_3X3_S2, true) TG_SET_ATTR(TG_CONVT_3X3_S2, false)
+    TG_SET_ATTR(TG_CONV_3X3, MODE_HALO) TG_SET_ATTR(TG_CONV_3X3, MODE_TAP) TG_SET_ATTR(TG_CONV_3X3, MODE_TAPN)
+    TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_HALO) TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_TAP)
 #undef TG_SET_ATTR
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_tcgen05: cudaFuncSetAttribute: %s",
@@ -763,12 +804,14 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->kind == TG_CONV_3X3) {
-    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, true><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
-    else        conv_tcgen05_kernel<TG_CONV_3X3, false><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+  if (tapn) {
+    conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+  } else if (d->kind == TG_CONV_3X3) {
+    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    else        conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
   } else {
-    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, true><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
-    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, false><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
   }
   TG_CUDA_LAUNCH_CHECK("conv_tcgen05");
   return TG_OK;

@@ -40,6 +40,8 @@ _SIGNATURES = {
     'tg_packed_weight_bytes': (c_size_t, [c_int, c_int]),
     'tg_pack_conv3x3_weights': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P]),
     'tg_pack_convT3x3s2_weights': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P]),
+    'tg_packed_weight_bytes_tapn': (c_size_t, [c_int]),
+    'tg_pack_conv3x3_weights_tapn': (c_int, [_P, c_int, c_int, _P, c_int, _P]),
     'tg_conv_tcgen05': (c_int, [ctypes.POINTER(ConvDesc), _P]),
     'tg_conv_simt': (c_int, [ctypes.POINTER(ConvDesc), _P]),
     'tg_warp_s2d_concat_hrflow': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -62,7 +62,8 @@ class PackedConv:
         else:
             self.cin_real, self.cout_real = weight.shape[0], weight.shape[1]
         self.cin = pad64(self.cin_real)
-        self.cout = pad64(self.cout_real) if epilogue == L.EPI_NHWC_F16 else 16
+        self.tapn = epilogue != L.EPI_NHWC_F16      # thin NCHW heads: tap-major N packing
+        self.cout = pad64(self.cout_real) if not self.tapn else 48
         self.packed = None
         self.bias = None
         self._ver = None
@@ -75,11 +76,15 @@ class PackedConv:
             return
         lib = L.load()
         w = _req(weight.detach(), torch.float32, 'weight', 4)
-        nbytes = lib.tg_packed_weight_bytes(self.cin, self.cout)
+        nbytes = (lib.tg_packed_weight_bytes_tapn(self.cin) if self.tapn
+                  else lib.tg_packed_weight_bytes(self.cin, self.cout))
         if self.packed is None:
             self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
             self.bias = torch.zeros(self.cout, dtype=torch.float32, device=w.device)
-        if self.kind == L.CONV_3X3:
+        if self.tapn:
+            rc = lib.tg_pack_conv3x3_weights_tapn(_ptr(w), self.cout_real, self.cin_real, _ptr(self.packed),
+                                                  self.cin, _stream())
+        elif self.kind == L.CONV_3X3:
             rc = lib.tg_pack_conv3x3_weights(_ptr(w), self.cout_real, self.cin_real, _ptr(self.packed),
                                              self.cout, self.cin, _stream())
         else:

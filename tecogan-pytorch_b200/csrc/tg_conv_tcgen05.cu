@@ -11,12 +11,12 @@
 //   B       : weights pre-packed on the device in the exact swizzled smem image
 //             (tg_pack_*_weights), either resident in smem for the whole kernel (SRNet, thin
 //             FNet layers) or streamed per (tap, chunk) with cp.async.bulk (fat FNet layers).
-//   D       : fp32 accumulators in TMEM, double buffered (epilogue of tile i overlaps the MMAs of
-//             tile i+1).  The transposed conv keeps 4 parity accumulators (1/2/2/4 taps) and
+//   D       : fp32 accumulators in TMEM, up to 8 buffers in flight (the epilogue of tile i overlaps
+//             the MMAs of tiles i+1..).  The transposed conv keeps 4 parity accumulators (1/2/2/4 taps) and
 //             stores them through 4 strided tensor maps = the pixel-shuffle interleave.
 //   roles   : warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//             warps 4..11 = epilogue (tcgen05.ld -> bias/act/residual -> fp16 -> swizzled smem
-//             -> TMA store; or the fused tanh*24 / bicubic-residual NCHW fp32 epilogues).
+//             warps 4..11 = two epilogue groups alternating tiles (tcgen05.ld -> bias/act/residual
+//             -> fp16 -> 128-byte NHWC row straight to global; or the thin-head TAPN epilogues).
 //
 // Replaces the nn.Conv2d / nn.ConvTranspose2d library calls K1, K10, K11, K12 of SURVEY.md 2.1.
 #include <cuda.h>
@@ -51,6 +51,7 @@ struct KParams {
   int box_w, box_h, org_x, org_y;
   int step_y, step_x;              // output pixels a tile advances by (16x8; 14x6 for MODE_TAPN)
   uint32_t acc_stride;             // TMEM columns per accumulator buffer
+  int n_buf;                       // accumulator buffers in flight (512 / acc_stride, <= 8, even)
   int n_stages;
   int n_split, bn;                 // output channels are split over n_split CTAs of bn columns
   uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
@@ -105,9 +106,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -125,22 +123,6 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
       : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const void* map, uint32_t src, int c0, int c1, int c2,
-                                             int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-      ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() {
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -237,11 +219,7 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
 // ------------------------------------------------------------------ the kernel
 template <int KIND, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
-                    const __grid_constant__ CUtensorMap map_y0,
-                    const __grid_constant__ CUtensorMap map_y1,
-                    const __grid_constant__ CUtensorMap map_y2,
-                    const __grid_constant__ CUtensorMap map_y3, const KParams p) {
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
@@ -255,27 +233,21 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
   // header: barriers
   const uint32_t bar_full = base;                       // [kMaxStages]
   const uint32_t bar_empty = base + 8 * kMaxStages;     // [kMaxStages]
-  const uint32_t bar_tfull = base + 16 * kMaxStages;    // [2]
-  const uint32_t bar_tempty = bar_tfull + 16;           // [2]
-  const uint32_t bar_b = bar_tempty + 16;               // [1]
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 48);
+  const uint32_t bar_tfull = base + 16 * kMaxStages;    // [8]
+  const uint32_t bar_tempty = bar_tfull + 64;           // [8]
+  const uint32_t bar_b = bar_tempty + 64;               // [1]
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 136);
   float* bias_s = reinterpret_cast<float*>(sm + 1024);
 
   const int epi_warps_active = 4;   // the 4 warps of the epilogue group that owns the buffer
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a);
-    if (d.epilogue == TG_EPI_NHWC_F16) {
-      tma_prefetch_desc(&map_y0);
-      if (p.n_acc == 4) { tma_prefetch_desc(&map_y1); tma_prefetch_desc(&map_y2); tma_prefetch_desc(&map_y3); }
-    }
-  }
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_a);
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < p.n_buf; ++b) {
       mbar_init(bar_tfull + 8 * b, 1);
       mbar_init(bar_tempty + 8 * b, epi_warps_active);
     }
@@ -341,25 +313,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       }
       if (timing) p.dbg[blockIdx.x * T_SLOTS + T_PROD_WAIT_EMPTY] = tw;
     }
-  } else if (warp == 1 || warp == 3) {
-    // ============================================================ MMA issuers
-    // HALO mode (one smem stage per tile): two issuer warps -- warp 1 owns accumulator buffer 0
-    // (even tiles of this CTA), warp 3 buffer 1 (odd tiles).  While one warp's MMAs occupy the
-    // tensor pipe the other is already polling the barriers of the next tile, so the fixed
-    // mbarrier / commit latencies between tiles are hidden.  A parity wait is only sound when the
-    // waiter is at most one phase ahead of the barrier; with one stage per tile the TMEM
-    // hand-shake (tile i+2 cannot start before the epilogue of tile i) guarantees that.  In the
-    // per-tap modes a tile spans more stages than the ring, so warp 1 alone issues every tile.
-    // Each warp walks its (warp-uniform) pipeline; one elected lane issues.
-    const bool dual = MODE != MODE_TAP && p.chunks == 1;
-    if (dual || warp == 1) {
-      const int mw = (dual && warp == 3) ? 1 : 0;
-      const int tstep = dual ? 2 : 1;
-      const int spt = (MODE != MODE_TAP ? 1 : 9) * p.chunks;      // smem stages consumed per tile
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    // One warp consumes the smem stages strictly in order (a parity wait is only sound while the
+    // waiter is at most one phase ahead of the barrier).  The fixed latencies between tiles
+    // (mbarrier polls, commit -> epilogue hand-off, MMA pipeline fill/drain) are hidden by depth
+    // instead: up to n_buf accumulator buffers are in flight in TMEM.  The warp walks the
+    // (warp-uniform) pipeline; one elected lane issues.
+    {
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
       uint32_t phase = 0;
-      int it = mw;
+      int it = 0;
       const uint32_t acc_stride = p.acc_stride;
       // descriptor templates: everything but the 14-bit start address is constant per kernel
       constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
@@ -370,14 +335,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       long long tw_tempty = 0, tw_full = 0, t_issue = 0;
       const long long t_mma0 = TG_T0();
-      for (int tile = blockIdx.x + mw * gridDim.x; tile < p.num_tiles; tile += tstep * gridDim.x, it += tstep) {
-        const int buf = it & 1;
-        const uint32_t bphase = (it >> 1) & 1;
-        {
-          const int gs = it * spt;                    // stages are filled in tile order
-          stage = gs % p.n_stages;
-          phase = (uint32_t)(gs / p.n_stages) & 1u;
-        }
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it % p.n_buf;
+        const uint32_t bphase = (uint32_t)(it / p.n_buf) & 1u;
         {
           const long long t0 = TG_T0();
           mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
@@ -450,7 +410,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
         if (elect_one_sync()) umma_commit(bar_tfull + 8 * buf);
         __syncwarp();
       }
-      if (timing && lane == 0 && mw == 0) {
+      if (timing && lane == 0) {
         unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
         o[T_MMA_WAIT_TEMPTY] = tw_tempty; o[T_MMA_WAIT_FULL] = tw_full; o[T_MMA_ISSUE] = t_issue;
         o[T_MMA_TOTAL] = clock64() - t_mma0; o[T_TILES] = it;
@@ -469,15 +429,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
     const int r = q * 32 + lane;   // row of the tile = TMEM lane
     const int ty = r >> 3, tx = r & 7;
     const uint32_t acc_stride = p.acc_stride;
-    const CUtensorMap* ymaps[4] = {&map_y0, &map_y1, &map_y2, &map_y3};
-    const uint32_t stg_base = p.off_staging + (uint32_t)group * 2u * 16384u;
-    uint32_t unit = 0;             // staging ring position of this group
-    const int buf = group;
     long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
     const long long t_epi0 = TG_T0();
     int it = group;
     for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
-      const uint32_t bphase = (it >> 1) & 1;
+      const int buf = it % p.n_buf;
+      const uint32_t bphase = (uint32_t)(it / p.n_buf) & 1u;
       const TileCoord tc = tile_coord(p, tile);
       // MODE_TAPN: thread = input position (halo ring included); interior positions are outputs
       const int py = tc.y0 + ty + (MODE == MODE_TAPN ? -1 : 0), px = tc.x0 + tx + (MODE == MODE_TAPN ? -1 : 0);
@@ -507,8 +464,14 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       t_s = TG_T0();
       tc_fence_after();
       if (d.epilogue == TG_EPI_NHWC_F16) {
-        for (int acc = 0; acc < p.n_acc; ++acc, ++unit) {
-          uint8_t* srow = sm + stg_base + (unit & 1u) * 16384u + r * 128;
+        // Each thread owns one output pixel = 64 channels = one contiguous 128-byte NHWC row: it
+        // goes straight from registers to global memory (8 x 16-byte stores complete the line),
+        // so the epilogue costs no shared-memory bandwidth -- the MMA operand reads need all of it.
+        for (int acc = 0; acc < p.n_acc; ++acc) {
+          int oy = py, ox = px, OW = d.w, OH = d.h;
+          if (KIND == TG_CONVT_3X3_S2) { oy = 2 * py + (acc >> 1); ox = 2 * px + (acc & 1); OW = 2 * d.w; OH = 2 * d.h; }
+          uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y) +
+                                                 (((size_t)tc.n * OH + oy) * OW + ox) * d.cout + tc.nb * p.bn);
 #pragma unroll
           for (int pc = 0; pc < 2; ++pc) {                // bn == 64: two 32-column pieces
             uint32_t v[32];
@@ -538,24 +501,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
                 }
                 o[j] = __floats2half2_rn(a0, a1);
               }
-              *reinterpret_cast<uint4*>(srow + (((pc * 4 + i) ^ (r & 7)) << 4)) =
-                  *reinterpret_cast<const uint4*>(o);
+              if (inb) orow[pc * 4 + i] = *reinterpret_cast<const uint4*>(o);
             }
           }
-          TG_ACC(te_compute, t_s);
-          t_s = TG_T0();
-          // the store issued one unit ago must have finished reading its buffer before the
-          // NEXT unit overwrites it; the barrier below publishes that to the whole group
-          if (gtid == 0) bulk_wait_read0();
-          fence_proxy_async_smem();     // generic-proxy smem writes -> visible to the TMA store
-          named_bar_sync(1 + group, 128);
-          if (gtid == 0) {
-            tma_store_4d(ymaps[acc], base + stg_base + (unit & 1u) * 16384u, tc.nb * p.bn, tc.x0, tc.y0, tc.n);
-            bulk_commit();
-          }
-          TG_ACC(te_store, t_s);
-          t_s = TG_T0();
         }
+        TG_ACC(te_compute, t_s);
       } else {
         // MODE_TAPN heads: D[pos][tap*4+co] = x[pos] . W[tap][co]; out[p] = sum_taps D[p+off(tap)][tap].
         // Positions exchange their nine float4 tap products through shared memory.
@@ -595,7 +545,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a,
       o[T_EPI_WAIT_STORE] = te_store_wait; o[T_EPI_WAIT_TFULL] = te_tfull; o[T_EPI_COMPUTE] = te_compute;
       o[T_EPI_STORE] = te_store; o[T_EPI_TOTAL] = clock64() - t_epi0;
     }
-    if (d.epilogue == TG_EPI_NHWC_F16 && gtid == 0) bulk_wait0();
   }
 
   // ------------------------------------------------------------ teardown
@@ -700,7 +649,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
 
   const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_tile_bytes;
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
-  uint32_t staging = tapn ? 4u * kTapnEBytes : 4u * 16384u;
+  uint32_t staging = tapn ? 4u * kTapnEBytes : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
@@ -729,6 +678,9 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
              "conv_tcgen05: per-CTA N must be 64 (48 for the thin heads)");
   TG_REQUIRE(!tapn || p.b_resident, TG_E_UNSUPPORTED, "conv_tcgen05: thin head weights must fit in smem");
   p.acc_stride = tapn ? 64u : (uint32_t)(p.n_acc * p.bn);
+  p.n_buf = (int)(kTmemCols / p.acc_stride);
+  if (p.n_buf > 8) p.n_buf = 8;
+  p.n_buf &= ~1;                        // even: epilogue group g owns the buffers of parity g
   if (tapn) {
     p.box_w = TW; p.box_h = TH; p.org_x = -1; p.org_y = -1;
     p.a_bytes = kTapABytes;
@@ -746,7 +698,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   }
   const uint32_t avail = kSmemLimit - fixed - (p.b_resident ? b_total : 0u);
   int stages = (int)(avail / p.stage_bytes);
-  const int want = p.halo ? 4 : kMaxStages;
+  const int want = p.halo ? 5 : kMaxStages;
   if (stages > want) stages = want;
   TG_REQUIRE(stages >= 2, TG_E_UNSUPPORTED, "conv_tcgen05: shared memory budget (cin=%d cout=%d)", d->cin, d->cout);
   p.n_stages = stages;
@@ -757,29 +709,10 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   TG_REQUIRE(smem_bytes <= kSmemLimit, TG_E_UNSUPPORTED, "conv_tcgen05: smem %u > limit", smem_bytes);
 
   // tensor maps
-  CUtensorMap map_a, map_y[4];
+  CUtensorMap map_a;
   rc = encode_nhwc(&map_a, d->x, d->cin, d->w, d->h, d->n, (size_t)d->cin, (size_t)d->w * d->cin,
                    (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
   if (rc != TG_OK) return rc;
-  if (!tapn) {
-    if (d->kind == TG_CONV_3X3) {
-      rc = encode_nhwc(&map_y[0], d->y, d->cout, d->w, d->h, d->n, (size_t)d->cout, (size_t)d->w * d->cout,
-                       (size_t)d->h * d->w * d->cout, 64, TW, TH);
-      if (rc != TG_OK) return rc;
-      map_y[1] = map_y[2] = map_y[3] = map_y[0];
-    } else {
-      const size_t OW = 2 * (size_t)d->w, OH = 2 * (size_t)d->h;
-      for (int a = 0; a < 4; ++a) {
-        const int py = a >> 1, px = a & 1;
-        const __half* yb = reinterpret_cast<const __half*>(d->y) + ((size_t)py * OW + px) * d->cout;
-        rc = encode_nhwc(&map_y[a], yb, d->cout, d->w, d->h, d->n, 2 * (size_t)d->cout, 2 * OW * d->cout,
-                         OH * OW * d->cout, 64, TW, TH);
-        if (rc != TG_OK) return rc;
-      }
-    }
-  } else {
-    map_y[0] = map_y[1] = map_y[2] = map_y[3] = map_a;   // unused
-  }
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
@@ -805,13 +738,13 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;
   if (tapn) {
-    conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
   } else if (d->kind == TG_CONV_3X3) {
-    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
-    else        conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
+    else        conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
   } else {
-    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
-    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, map_y[0], map_y[1], map_y[2], map_y[3], p);
+    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
+    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
   }
   TG_CUDA_LAUNCH_CHECK("conv_tcgen05");
   return TG_OK;

@@ -124,6 +124,16 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+// 256-bit global store (sm_100+): one full 32-byte sector per thread-store, streaming (no L1
+// allocation) -- half the LSU transactions of two 128-bit stores
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr),
+               "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
@@ -484,9 +494,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
               if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
             }
             const float4* bias4 = reinterpret_cast<const float4*>(bias_s + tc.nb * p.bn + pc * 32);
+            uint4 ov[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              __align__(16) __half2 o[4];
+              __half2* o = reinterpret_cast<__half2*>(&ov[i]);
               const __half2* rh = reinterpret_cast<const __half2*>(&res[pc * 4 + i]);
               const float4 b0 = bias4[i * 2], b1 = bias4[i * 2 + 1];
               const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
@@ -501,7 +512,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
                 }
                 o[j] = __floats2half2_rn(a0, a1);
               }
-              if (inb) orow[pc * 4 + i] = *reinterpret_cast<const uint4*>(o);
+            }
+            if (inb) {
+              st_global_256(orow + pc * 4, ov[0], ov[1]);
+              st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
             }
           }
         }
@@ -656,7 +670,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   const uint32_t halo_stage = (halo_bytes + 1023u) & ~1023u;
   uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
 
-  const bool can_resident_halo = fixed + b_total + 2u * halo_stage <= kSmemLimit;
+  const bool can_resident_halo = d->cout <= 64 && fixed + b_total + 2u * halo_stage <= kSmemLimit;
   // cout > 64 only occurs on the low-resolution FNet layers: few spatial tiles, so stream the
   // weights and split N over CTAs instead of making every CTA load all of them
   const bool can_resident_tap = d->cout <= 64 && fixed + b_total + 2u * kTapABytes <= kSmemLimit;

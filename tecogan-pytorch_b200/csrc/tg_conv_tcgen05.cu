@@ -21,6 +21,7 @@
 // Replaces the nn.Conv2d / nn.ConvTranspose2d library calls K1, K10, K11, K12 of SURVEY.md 2.1.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "tg_common.cuh"
@@ -345,48 +346,66 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       long long tw_tempty = 0, tw_full = 0, t_issue = 0;
       const long long t_mma0 = TG_T0();
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int buf = it % p.n_buf;
-        const uint32_t bphase = (uint32_t)(it / p.n_buf) & 1u;
-        {
-          const long long t0 = TG_T0();
-          mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
-          TG_ACC(tw_tempty, t0);
-        }
+      // Software-pipelined barrier polling: the barriers of the NEXT smem stage (and, at a tile
+      // boundary, the next tile's TMEM buffer) are polled while MMAs of the current stage are still
+      // queued in the tensor pipe, so the poll latencies (~100-200 cycles each) do not drain it.
+      int buf = 0;
+      uint32_t bphase = 0;
+      if (blockIdx.x < p.num_tiles) {
+        mbar_wait(bar_tempty, 1, 4);              // fresh barrier: passes immediately
+        mbar_wait(bar_full, 0, 5);
         tc_fence_after();
+      }
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const bool has_next = tile + (int)gridDim.x < p.num_tiles;
+        const int nbuf = (buf + 1 == p.n_buf) ? 0 : buf + 1;
+        const uint32_t nbphase = (buf + 1 == p.n_buf) ? (bphase ^ 1u) : bphase;
         const uint32_t d_base = tmem_base + buf * acc_stride;
         if (MODE != MODE_TAP) {
           constexpr int NG = MODE == MODE_TAPN ? 1 : 9;   // TAPN: one group, all taps live in N
+          constexpr int NG_HEAD = NG > 2 ? NG - 2 : 0;    // groups issued before the look-ahead poll
           for (int c = 0; c < p.chunks; ++c) {
-            {
-              const long long t0 = TG_T0();
-              mbar_wait(bar_full + 8 * stage, phase, 5);
-              TG_ACC(tw_full, t0);
-            }
-            tc_fence_after();
+            const bool last = c == p.chunks - 1;
+            const int nstage = (stage + 1 == p.n_stages) ? 0 : stage + 1;
+            const uint32_t nphase = (stage + 1 == p.n_stages) ? (phase ^ 1u) : phase;
             const uint32_t sa16 = ((smem_stage0 + stage * p.stage_bytes) & 0x3FFFFu) >> 4;
             const long long t_i0 = TG_T0();
-            if (elect_one_sync()) {
 #pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              const TgGroup gr = MODE == MODE_TAPN ? TgGroup{0, 0, 0, 0, 0} : tg_group(KIND, g);
-              // first MMA into an accumulator (per tile) overwrites, the rest accumulate
-              const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
-              const uint32_t a16 = MODE == MODE_TAPN
-                                       ? sa16
-                                       : sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
-              const uint32_t b16 = smem_b16 + (uint32_t)(g * p.chunks + c) * btb16;
-              const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
+            for (int part = 0; part < 2; ++part) {
+              if (elect_one_sync()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
-                         (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
+                for (int g = (part == 0 ? 0 : NG_HEAD); g < (part == 0 ? NG_HEAD : NG); ++g) {
+                  const TgGroup gr = MODE == MODE_TAPN ? TgGroup{0, 0, 0, 0, 0} : tg_group(KIND, g);
+                  // first MMA into an accumulator (per tile) overwrites, the rest accumulate
+                  const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
+                  const uint32_t a16 = MODE == MODE_TAPN
+                                           ? sa16
+                                           : sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
+                  const uint32_t b16 = smem_b16 + (uint32_t)(g * p.chunks + c) * btb16;
+                  const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
+                             (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
+                }
+                if (part == 1) {
+                  umma_commit(bar_empty + 8 * stage);
+                  if (last) umma_commit(bar_tfull + 8 * buf);
+                }
+              }
+              __syncwarp();
+              if (part == 0) {
+                TG_ACC(t_issue, t_i0);
+                if (!last || has_next) {
+                  long long t0 = TG_T0();
+                  if (last) { mbar_wait(bar_tempty + 8 * nbuf, nbphase ^ 1, 4); TG_ACC(tw_tempty, t0); t0 = TG_T0(); }
+                  mbar_wait(bar_full + 8 * nstage, nphase, 5);
+                  TG_ACC(tw_full, t0);
+                  tc_fence_after();
+                }
+              }
             }
-            umma_commit(bar_empty + 8 * stage);
-            }
-            __syncwarp();
-            TG_ACC(t_issue, t_i0);
-            if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+            stage = nstage; phase = nphase;
           }
         } else {
 #pragma unroll
@@ -395,12 +414,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
             const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
             for (int c = 0; c < p.chunks; ++c) {
-              {
-                const long long t0 = TG_T0();
-                mbar_wait(bar_full + 8 * stage, phase, 6);
-                TG_ACC(tw_full, t0);
-              }
-              tc_fence_after();
+              const bool last = g == 8 && c == p.chunks - 1;
+              const int nstage = (stage + 1 == p.n_stages) ? 0 : stage + 1;
+              const uint32_t nphase = (stage + 1 == p.n_stages) ? (phase ^ 1u) : phase;
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
               const uint32_t a16 = (sa & 0x3FFFFu) >> 4;
               const uint32_t b16 = p.b_resident ? smem_b16 + (uint32_t)(g * p.chunks + c) * btb16
@@ -411,14 +427,22 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
                   umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
                            (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
                 umma_commit(bar_empty + 8 * stage);
+                if (last) umma_commit(bar_tfull + 8 * buf);
               }
               __syncwarp();
-              if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
+              // look ahead: poll the next stage while the 4 MMAs just issued execute
+              if (!last || has_next) {
+                long long t0 = TG_T0();
+                if (last) { mbar_wait(bar_tempty + 8 * nbuf, nbphase ^ 1, 4); TG_ACC(tw_tempty, t0); t0 = TG_T0(); }
+                mbar_wait(bar_full + 8 * nstage, nphase, 6);
+                TG_ACC(tw_full, t0);
+                tc_fence_after();
+              }
+              stage = nstage; phase = nphase;
             }
           }
         }
-        if (elect_one_sync()) umma_commit(bar_tfull + 8 * buf);
-        __syncwarp();
+        buf = nbuf; bphase = nbphase;
       }
       if (timing && lane == 0) {
         unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
@@ -695,6 +719,10 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.n_buf = (int)(kTmemCols / p.acc_stride);
   if (p.n_buf > 8) p.n_buf = 8;
   p.n_buf &= ~1;                        // even: epilogue group g owns the buffers of parity g
+  if (const char* e = getenv("TG_DBG_NBUF")) {   // diagnostics only (tools/conv_timers.py)
+    const int v = atoi(e) & ~1;
+    if (v >= 2 && v <= p.n_buf) p.n_buf = v;
+  }
   if (tapn) {
     p.box_w = TW; p.box_h = TH; p.org_x = -1; p.org_y = -1;
     p.a_bytes = kTapABytes;

@@ -33,95 +33,110 @@ __device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, 
          v11 * ax * ay;
 }
 
-// One CTA = one LR row x LRW=128/S LR pixels = S HR rows x 128 HR columns; 128*S threads, thread
-// (X = tid%128, sy = tid/128) owns ONE HR pixel: 2 flow values, then 4 corner gathers per channel
-// (low register count -> full occupancy, ~14 independent loads in flight per thread).
-//   LRFLOW: the LR flow neighbourhood (4 rows x LRW+3 cols, reflect-padded + replicate-clamped) is
-//   staged in smem once, the x-pass of the separable 4-tap upsampler is evaluated once per
-//   (LR row, HR column) and shared by the S HR rows, the y-pass per thread.
-template <int S, bool LRFLOW>
-__global__ void __launch_bounds__(128 * S)
+// One CTA = RY LR rows x LRW=128/S LR pixels; 128 threads, thread t owns HR column X = x0*S + t and
+// walks the S HR rows of each LR row (S*RY pixels per thread -> enough independent gathers in
+// flight per thread, few CTAs -> little launch overhead).
+//   LRFLOW: the LR flow neighbourhood ((RY+3) rows x LRW+3 cols, reflect-padded + replicate-clamped)
+//   is staged in smem once; each thread evaluates the x-pass of the separable 4-tap upsampler for its
+//   own column into registers (RY+3 values per component) and the y-pass per HR row.
+template <int S, bool LRFLOW, int RY>
+__global__ void __launch_bounds__(128)
 warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                        const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
                        int w, int h8, int w8, int up_mode, int cpad) {
   constexpr int LRW = 128 / S;
-  constexpr int NT = 128 * S;
   constexpr int FW = LRW + 3;                 // LR columns x0-1 .. x0+LRW+1
+  constexpr int FH = RY + 3;                  // LR rows    y0-1 .. y0+RY+1
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* tile = reinterpret_cast<__half*>(smem_raw);  // [LRW][cpad]
-  __shared__ float fsrc[LRFLOW ? 2 * 4 * FW : 1];      // [comp][row i][col]
-  __shared__ float hpass[LRFLOW ? 2 * 4 * 128 : 1];    // [comp][row i][X]
+  __shared__ float fsrc[LRFLOW ? 2 * FH * FW : 1];     // [comp][row][col]
 
-  const int tid = threadIdx.x;
-  const int t = tid & 127, sy = tid >> 7;
+  const int t = threadIdx.x;
   const int x0 = blockIdx.x * LRW;      // first LR column of the tile
-  const int y = blockIdx.y;             // LR row
+  const int y0 = blockIdx.y * RY;       // first LR row
   const int n = blockIdx.z;
   const int H = h * S, W = w * S;
   const int X = x0 * S + t;             // HR column of this thread
   const int lx = t / S, sx = t - lx * S;
-
-  // zero the pad channels [ (S*S+1)*C, cpad ) and stage lr_curr
   const int used = (S * S + 1) * C;
-  for (int i = tid; i < LRW * (cpad - used); i += NT) {
-    const int p = i / (cpad - used), k = i - p * (cpad - used);
-    tile[p * cpad + used + k] = __float2half(0.f);
-  }
-  for (int i = tid; i < LRW * C; i += NT) {
-    const int k = i / LRW, p = i - k * LRW;
-    const int xx = x0 + p;
-    float v = 0.f;
-    if (xx < w) v = __ldg(lr_curr + (((size_t)n * C + k) * h + y) * w + xx);
-    tile[p * cpad + k] = __float2half(v);
-  }
 
-  float u = 0.f, v = 0.f;
+  float hx[2][FH];                      // x-pass of the flow upsampler, this thread's column
   if (LRFLOW) {
     // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
-    for (int i = tid; i < 2 * 4 * FW; i += NT) {
-      const int col = i % FW, row = (i / FW) & 3, comp = i / (4 * FW);
-      const int yy = tg_reflect_hi(tg_clampi(y - 1 + row, 0, h - 1), h8);
+    for (int i = t; i < 2 * FH * FW; i += 128) {
+      const int col = i % FW, row = (i / FW) % FH, comp = i / (FH * FW);
+      const int yy = tg_reflect_hi(tg_clampi(y0 - 1 + row, 0, h - 1), h8);
       const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), w8);
       fsrc[i] = __ldg(flow + (((size_t)n * 2 + comp) * h8 + yy) * w8 + xx);
     }
     __syncthreads();
-    for (int i = tid; i < 2 * 4 * 128; i += NT) {
-      const int xcol = i & 127, row = (i >> 7) & 3, comp = i >> 9;
-      float kx[4];
-      tg_up_taps(up_mode, xcol % S, S, kx);
-      const float* f = fsrc + (comp * 4 + row) * FW + xcol / S;   // taps at LR cols lx-1 .. lx+2
-      hpass[i] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
+    float kx[4];
+    tg_up_taps(up_mode, sx, S, kx);
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp)
+#pragma unroll
+      for (int row = 0; row < FH; ++row) {
+        const float* f = fsrc + (comp * FH + row) * FW + lx;   // taps at LR cols lx-1 .. lx+2
+        hx[comp][row] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
+      }
+  }
+
+#pragma unroll
+  for (int ry = 0; ry < RY; ++ry) {
+    const int y = y0 + ry;
+    if (y >= h) break;                  // uniform over the CTA
+    // zero the pad channels [ (S*S+1)*C, cpad ) and stage lr_curr
+    for (int i = t; i < LRW * (cpad - used); i += 128) {
+      const int p = i / (cpad - used), k = i - p * (cpad - used);
+      tile[p * cpad + used + k] = __float2half(0.f);
+    }
+    for (int i = t; i < LRW * C; i += 128) {
+      const int k = i / LRW, p = i - k * LRW;
+      const int xx = x0 + p;
+      float v = 0.f;
+      if (xx < w) v = __ldg(lr_curr + (((size_t)n * C + k) * h + y) * w + xx);
+      tile[p * cpad + k] = __float2half(v);
+    }
+    if (X < W) {
+      float u[S], v[S];
+      if (LRFLOW) {
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy) {
+          float ky[4];
+          tg_up_taps(up_mode, sy, S, ky);
+          u[sy] = (float)S * (ky[0] * hx[0][ry] + ky[1] * hx[0][ry + 1] + ky[2] * hx[0][ry + 2] + ky[3] * hx[0][ry + 3]);
+          v[sy] = (float)S * (ky[0] * hx[1][ry] + ky[1] * hx[1][ry + 1] + ky[2] * hx[1][ry + 2] + ky[3] * hx[1][ry + 3]);
+        }
+      } else {
+        const float* f0 = flow + (((size_t)n * 2 + 0) * H + (size_t)y * S) * W + X;
+        const float* f1 = flow + (((size_t)n * 2 + 1) * H + (size_t)y * S) * W + X;
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy) {
+          u[sy] = __ldg(f0 + (size_t)sy * W);
+          v[sy] = __ldg(f1 + (size_t)sy * W);
+        }
+      }
+#pragma unroll
+      for (int sy = 0; sy < S; ++sy) {
+        const float fx = (float)X + u[sy];
+        const float fy = (float)(y * S + sy) + v[sy];
+        // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
+        __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
+        for (int k = 0; k < C; ++k) {
+          const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
+          dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+        }
+      }
     }
     __syncthreads();
-    float ky[4];
-    tg_up_taps(up_mode, sy, S, ky);
-    u = (float)S * (ky[0] * hpass[0 * 128 + t] + ky[1] * hpass[1 * 128 + t] +
-                    ky[2] * hpass[2 * 128 + t] + ky[3] * hpass[3 * 128 + t]);
-    v = (float)S * (ky[0] * hpass[4 * 128 + t] + ky[1] * hpass[5 * 128 + t] +
-                    ky[2] * hpass[6 * 128 + t] + ky[3] * hpass[7 * 128 + t]);
-  } else if (X < W) {
-    const size_t o = ((size_t)y * S + sy) * W + X;
-    u = __ldg(flow + ((size_t)n * 2 + 0) * H * W + o);
-    v = __ldg(flow + ((size_t)n * 2 + 1) * H * W + o);
+    // coalesced store of min(LRW, w-x0) pixels * cpad halves (cpad*2 bytes, multiple of 16)
+    const int npx = min(LRW, w - x0);
+    const int vec_per_px = cpad / 8;  // uint4 per pixel
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    uint4* dstg = reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0) * cpad);
+    for (int i = t; i < npx * vec_per_px; i += 128) dstg[i] = src[i];
+    __syncthreads();
   }
-  if (X < W) {
-    const float fx = (float)X + u;
-    const float fy = (float)(y * S + sy) + v;
-    // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
-    __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
-    for (int k = 0; k < C; ++k) {
-      const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
-      dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
-    }
-  }
-  __syncthreads();
-
-  // coalesced store of min(LRW, w-x0) pixels * cpad halves (cpad*2 bytes, multiple of 16)
-  const int npx = min(LRW, w - x0);
-  const int vec_per_px = cpad / 8;  // uint4 per pixel
-  const uint4* src = reinterpret_cast<const uint4*>(tile);
-  uint4* dstg = reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0) * cpad);
-  for (int i = tid; i < npx * vec_per_px; i += NT) dstg[i] = src[i];
 }
 
 // =====================================================================================
@@ -272,47 +287,54 @@ __global__ void space_to_depth_kernel(const float* __restrict__ x, float* __rest
   }
 }
 
-// y = mul * upsample_func(reflect_pad(x)): one CTA = one LR row x 128/S LR pixels of one plane ->
-// S HR rows x 128 HR columns; separable 4-tap filter through shared memory (see tg_up_taps).
-template <int S>
-__global__ void __launch_bounds__(128 * S)
+// y = mul * upsample_func(reflect_pad(x)): one CTA = RY LR rows x 128/S LR pixels of one plane ->
+// RY*S HR rows x 128 HR columns; thread t owns HR column X: x-pass of the separable 4-tap filter
+// (tg_up_taps) for RY+3 source rows into registers, then RY*S outputs (512-byte coalesced rows).
+template <int S, int RY>
+__global__ void __launch_bounds__(128)
 upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int hin, int win, int h,
                      int w, int up_mode, float mul) {
   constexpr int LRW = 128 / S;
-  constexpr int FW = LRW + 3;
-  __shared__ float fsrc[4 * FW];
-  __shared__ float hpass[4 * 128];
-  const int tid = threadIdx.x, t = tid & 127, sy = tid >> 7;
-  const int x0 = blockIdx.x * LRW, yl = blockIdx.y;
+  constexpr int FW = LRW + 3, FH = RY + 3;
+  __shared__ float fsrc[FH * FW];
+  const int t = threadIdx.x;
+  const int x0 = blockIdx.x * LRW, y0 = blockIdx.y * RY;
   const size_t pl = blockIdx.z;
   const float* src = x + pl * hin * win;
-  for (int i = tid; i < 4 * FW; i += 128 * S) {
+  for (int i = t; i < FH * FW; i += 128) {
     const int col = i % FW, row = i / FW;
-    const int yy = tg_reflect_hi(tg_clampi(yl - 1 + row, 0, h - 1), hin);
+    const int yy = tg_reflect_hi(tg_clampi(y0 - 1 + row, 0, h - 1), hin);
     const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), win);
     fsrc[i] = __ldg(src + (size_t)yy * win + xx);
   }
   __syncthreads();
-  {
-    // x-pass: 4 LR rows x 128 HR columns, 128*S threads -> 4/S rows per thread
-    float kx[4];
-    tg_up_taps(up_mode, t % S, S, kx);
-    for (int row = sy; row < 4; row += S) {
-      const float* f = fsrc + row * FW + t / S;
-      hpass[row * 128 + t] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
-    }
-  }
-  __syncthreads();
   const int X = x0 * S + t;
-  if (X < w * S) {
-    float ky[4];
-    tg_up_taps(up_mode, sy, S, ky);
-    const float v = ky[0] * hpass[t] + ky[1] * hpass[128 + t] + ky[2] * hpass[256 + t] + ky[3] * hpass[384 + t];
-    y[(pl * h * S + (size_t)yl * S + sy) * ((size_t)w * S) + X] = mul * v;
+  if (X >= w * S) return;
+  float kx[4], hx[FH];
+  tg_up_taps(up_mode, t % S, S, kx);
+#pragma unroll
+  for (int row = 0; row < FH; ++row) {
+    const float* f = fsrc + row * FW + t / S;
+    hx[row] = kx[0] * f[0] + kx[1] * f[1] + kx[2] * f[2] + kx[3] * f[3];
+  }
+  float* dst = y + (pl * h * S + (size_t)y0 * S) * ((size_t)w * S) + X;
+#pragma unroll
+  for (int ry = 0; ry < RY; ++ry) {
+    if (y0 + ry >= h) break;
+#pragma unroll
+    for (int sy = 0; sy < S; ++sy) {
+      float ky[4];
+      tg_up_taps(up_mode, sy, S, ky);
+      dst[(size_t)(ry * S + sy) * ((size_t)w * S)] =
+          mul * (ky[0] * hx[ry] + ky[1] * hx[ry + 1] + ky[2] * hx[ry + 2] + ky[3] * hx[ry + 3]);
+    }
   }
 }
 
 // float32_to_uint8 + CHW->HWC: uint8(clip(rint(x*255),0,255)), rint = round-half-even
+__device__ __forceinline__ uint32_t tg_q8(float v) {
+  return (uint32_t)fminf(fmaxf(rintf(v * 255.f), 0.f), 255.f);
+}
 __global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, int c,
                                 int h, int w) {
   const size_t hw = (size_t)h * w;
@@ -321,11 +343,25 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict
        i += (size_t)gridDim.x * blockDim.x) {
     const int nn = (int)(i / hw);
     const size_t sp = i % hw;
-    for (int k = 0; k < c; ++k) {
-      const float v = __ldg(x + ((size_t)nn * c + k) * hw + sp) * 255.f;
-      const float r = fminf(fmaxf(rintf(v), 0.f), 255.f);
-      y[i * c + k] = (uint8_t)r;
-    }
+    for (int k = 0; k < c; ++k) y[i * c + k] = (uint8_t)tg_q8(__ldg(x + ((size_t)nn * c + k) * hw + sp));
+  }
+}
+// c == 3, hw % 4 == 0: one thread = 4 pixels = three float4 loads -> 12 bytes = three u32 stores
+__global__ void to_uint8_c3x4_kernel(const float4* __restrict__ x, uint32_t* __restrict__ y, int n,
+                                     size_t hw4) {
+  const size_t total = (size_t)n * hw4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t nn = i / hw4, sp = i % hw4;
+    const float4 r = __ldg(x + (nn * 3 + 0) * hw4 + sp);
+    const float4 g = __ldg(x + (nn * 3 + 1) * hw4 + sp);
+    const float4 b = __ldg(x + (nn * 3 + 2) * hw4 + sp);
+    // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+    const uint32_t w0 = tg_q8(r.x) | (tg_q8(g.x) << 8) | (tg_q8(b.x) << 16) | (tg_q8(r.y) << 24);
+    const uint32_t w1 = tg_q8(g.y) | (tg_q8(b.y) << 8) | (tg_q8(r.z) << 16) | (tg_q8(g.z) << 24);
+    const uint32_t w2 = tg_q8(b.z) | (tg_q8(r.w) << 8) | (tg_q8(g.w) << 16) | (tg_q8(b.w) << 24);
+    uint32_t* o = y + i * 3;
+    o[0] = w0; o[1] = w1; o[2] = w2;
   }
 }
 
@@ -359,15 +395,16 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int lrw = 128 / s;
-  dim3 grid(tg_ceil_div(w, lrw), h, n);
+  constexpr int RY = 2;
+  dim3 grid(tg_ceil_div(w, lrw), tg_ceil_div(h, RY), n);
   const size_t smem = (size_t)lrw * cpad * sizeof(__half);
   __half* o = (__half*)out;
   if (s == 4) {
-    if (lrflow) warp_s2d_concat_kernel<4, true><<<grid, 512, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<4, false><<<grid, 512, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) warp_s2d_concat_kernel<4, true, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<4, false, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   } else {
-    if (lrflow) warp_s2d_concat_kernel<2, true><<<grid, 256, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<2, false><<<grid, 256, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) warp_s2d_concat_kernel<2, true, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        warp_s2d_concat_kernel<2, false, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   }
   TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
   return TG_OK;
@@ -475,9 +512,10 @@ int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int wi
   TG_REQUIRE(up_mode == TG_UP_BICUBIC || up_mode == TG_UP_BILINEAR, TG_E_INVALID, "upsample: up_mode");
   TG_REQUIRE(s == 2 || s == 4, TG_E_UNSUPPORTED, "upsample: scale %d (2 or 4)", s);
   TG_REQUIRE(h <= 65535 && (size_t)n * c <= 65535, TG_E_UNSUPPORTED, "upsample: grid too large");
-  dim3 grid(tg_ceil_div(w, 128 / s), h, n * c);
-  if (s == 4) upsample_nchw_kernel<4><<<grid, 512, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
-  else        upsample_nchw_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
+  constexpr int RY = 4;
+  dim3 grid(tg_ceil_div(w, 128 / s), tg_ceil_div(h, RY), n * c);
+  if (s == 4) upsample_nchw_kernel<4, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
+  else        upsample_nchw_kernel<2, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
   TG_CUDA_LAUNCH_CHECK("upsample");
   return TG_OK;
 }
@@ -486,7 +524,11 @@ int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int 
   TG_REQUIRE(x && y, TG_E_INVALID, "float_to_uint8: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "float_to_uint8: bad shape");
   const size_t total = (size_t)n * h * w;
-  to_uint8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
+  if (c == 3 && ((size_t)h * w) % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 3) == 0)
+    to_uint8_c3x4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, (uint32_t*)y, n, (size_t)h * w / 4);
+  else
+    to_uint8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
   TG_CUDA_LAUNCH_CHECK("float_to_uint8");
   return TG_OK;
 }

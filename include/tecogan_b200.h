@@ -46,7 +46,7 @@ enum { TG_UP_BICUBIC = 0, TG_UP_BILINEAR = 1 };
 enum {
   TG_EPI_NHWC_F16 = 0,      /* y = act(conv + bias) [+ residual]  -> NHWC fp16        */
   TG_EPI_FLOW_NCHW_F32 = 1, /* y = 24*tanh(conv + bias)           -> NCHW fp32 [N,2,H,W] */
-  TG_EPI_OUT_NCHW_F32 = 2   /* y += conv + bias (y pre-filled)    -> NCHW fp32 [N,C,H,W] */
+  TG_EPI_OUT_NCHW_F32 = 2   /* y = conv + bias                    -> NCHW fp32 [N,C,H,W] */
 };
 enum { TG_AMODE_AUTO = 0, TG_AMODE_HALO = 1, TG_AMODE_TAP = 2 };
 
@@ -81,8 +81,9 @@ int tg_pack_conv3x3_weights_tapn(const float* w_oihw, int cout, int cin, void* p
  * 3x3 convolution / stride-2 transposed convolution as tcgen05 implicit GEMM.
  * Replaces nn.Conv2d+activation (tecogan_nets.py:23-65, 92-98, 111-116, 131),
  * nn.ConvTranspose2d+ReLU (:119-126), torch.tanh(.)*24 (:80) and the add of
- * `out += upsample_func(lr_curr)` (:145): the caller pre-fills y with
- * tg_upsample_nchw_f32(lr_curr) and TG_EPI_OUT_NCHW_F32 accumulates conv+bias into it.
+ * `out += upsample_func(lr_curr)` (:145): TG_EPI_OUT_NCHW_F32 stores conv+bias and the caller
+ * then runs tg_upsample_nchw_f32(lr_curr, accumulate=1) on the same buffer (the epilogue is a pure
+ * store: a read-modify-write there exposes a global-load round trip per tile).
  * ---------------------------------------------------------------------- */
 typedef struct tg_conv_desc {
   const void* x;        /* NHWC fp16 [n,h,w,cin]                                         */
@@ -142,11 +143,12 @@ int tg_backward_warp_nchw_f32(const float* x, const float* flow, float* y, int n
                               int w, void* stream);                      /* net_utils.py:50-82  */
 int tg_space_to_depth_nchw_f32(const float* x, float* y, int n, int c, int h, int w, int s,
                                void* stream);                            /* net_utils.py:36-47  */
-/* y = mul * upsample(reflect_pad(x -> (h,w)))  ; x [n,c,hin,win], hin<=h, win<=w.
+/* y = [y +] mul * upsample(reflect_pad(x -> (h,w)))  ; x [n,c,hin,win], hin<=h, win<=w;
+ * accumulate != 0 adds into y (fp32).
  * up_mode bicubic = BicubicUpsampler (net_utils.py:101-156), bilinear = F.interpolate
  * (net_utils.py:87-89).  hin==h, win==w, mul==1 gives the plain upsample_func. */
 int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int win, int h, int w,
-                         int s, int up_mode, float mul, void* stream);
+                         int s, int up_mode, float mul, int accumulate, void* stream);
 int tg_nchw_f32_to_nhwc_f16(const float* x, void* y, int n, int c, int h, int w, int cpad,
                             int c_offset, void* stream);
 int tg_nhwc_f16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w, int cpad,

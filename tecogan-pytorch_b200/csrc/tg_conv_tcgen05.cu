@@ -53,6 +53,7 @@ struct KParams {
   int step_y, step_x;              // output pixels a tile advances by (16x8; 14x6 for MODE_TAPN)
   uint32_t acc_stride;             // TMEM columns per accumulator buffer
   int n_buf;                       // accumulator buffers in flight (512 / acc_stride, <= 8, even)
+  int dbg_flags;                   // diagnostics (TG_DBG_FLAGS): 1 = TAPN skip global RMW, 2 = skip exchange
   int n_stages;
   int n_split, bn;                 // output channels are split over n_split CTAs of bn columns
   uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
@@ -478,7 +479,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       // operands that come from global memory are fetched BEFORE waiting for the accumulator so
       // their latency hides behind the MMAs of this tile
       uint4 res[8];
-      float yprev[4];
       const bool has_res = (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(
@@ -486,12 +486,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
 #pragma unroll
         for (int i = 0; i < 8; ++i) res[i] = __ldg(rp + i);
-      }
-      if (d.epilogue == TG_EPI_OUT_NCHW_F32 && inb) {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          if (ch < d.cout_real)
-            yprev[ch] = reinterpret_cast<const float*>(d.y)[(((size_t)tc.n * d.cout_real + ch) * d.h + py) * d.w + px];
       }
       mbar_wait(bar_tfull + 8 * buf, bphase, 7);
       TG_ACC(te_tfull, t_s);
@@ -556,13 +550,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it >> 1) & 1)) * kTapnEBytes);
+        if (!(p.dbg_flags & 2))
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
           E[r * 9 + tap] = make_float4(__uint_as_float(v[tap * 4]), __uint_as_float(v[tap * 4 + 1]),
                                        __uint_as_float(v[tap * 4 + 2]), __uint_as_float(v[tap * 4 + 3]));
-        named_bar_sync(1 + group, 128);
-        if (inb) {
+        if (!(p.dbg_flags & 2)) named_bar_sync(1 + group, 128);
+        if (inb && !(p.dbg_flags & 1)) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!(p.dbg_flags & 2))
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const float4 e = E[(r + (tap / 3 - 1) * TW + (tap % 3 - 1)) * 9 + tap];
@@ -572,7 +568,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             if (d.epilogue == TG_EPI_FLOW_NCHW_F32) tg_epi_flow(d, tc.n, py, px, d.h, d.w, ch, av[ch]);
-            else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, av[ch], yprev[ch]);
+            else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, av[ch]);
           }
         }
         TG_ACC(te_compute, t_s);
@@ -719,6 +715,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.n_buf = (int)(kTmemCols / p.acc_stride);
   if (p.n_buf > 8) p.n_buf = 8;
   p.n_buf &= ~1;                        // even: epilogue group g owns the buffers of parity g
+  p.dbg_flags = 0;
+  if (const char* e = getenv("TG_DBG_FLAGS")) p.dbg_flags = atoi(e);
   if (const char* e = getenv("TG_DBG_NBUF")) {   // diagnostics only (tools/conv_timers.py)
     const int v = atoi(e) & ~1;
     if (v >= 2 && v <= p.n_buf) p.n_buf = v;

@@ -293,7 +293,7 @@ __global__ void space_to_depth_kernel(const float* __restrict__ x, float* __rest
 template <int S, int RY>
 __global__ void __launch_bounds__(128)
 upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int hin, int win, int h,
-                     int w, int up_mode, float mul) {
+                     int w, int up_mode, float mul, int accumulate) {
   constexpr int LRW = 128 / S;
   constexpr int FW = LRW + 3, FH = RY + 3;
   __shared__ float fsrc[FH * FW];
@@ -325,8 +325,9 @@ upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int hin
     for (int sy = 0; sy < S; ++sy) {
       float ky[4];
       tg_up_taps(up_mode, sy, S, ky);
-      dst[(size_t)(ry * S + sy) * ((size_t)w * S)] =
-          mul * (ky[0] * hx[ry] + ky[1] * hx[ry + 1] + ky[2] * hx[ry + 2] + ky[3] * hx[ry + 3]);
+      float* o = dst + (size_t)(ry * S + sy) * ((size_t)w * S);
+      const float up = mul * (ky[0] * hx[ry] + ky[1] * hx[ry + 1] + ky[2] * hx[ry + 2] + ky[3] * hx[ry + 3]);
+      *o = accumulate ? *o + up : up;
     }
   }
 }
@@ -504,7 +505,7 @@ int tg_space_to_depth_nchw_f32(const float* x, float* y, int n, int c, int h, in
 }
 
 int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int win, int h, int w,
-                         int s, int up_mode, float mul, void* stream) {
+                         int s, int up_mode, float mul, int accumulate, void* stream) {
   TG_REQUIRE(x && y, TG_E_INVALID, "upsample: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && hin > 0 && win > 0 && h >= hin && w >= win, TG_E_INVALID,
              "upsample: bad shape");
@@ -514,8 +515,8 @@ int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int wi
   TG_REQUIRE(h <= 65535 && (size_t)n * c <= 65535, TG_E_UNSUPPORTED, "upsample: grid too large");
   constexpr int RY = 4;
   dim3 grid(tg_ceil_div(w, 128 / s), tg_ceil_div(h, RY), n * c);
-  if (s == 4) upsample_nchw_kernel<4, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
-  else        upsample_nchw_kernel<2, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul);
+  if (s == 4) upsample_nchw_kernel<4, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul, accumulate);
+  else        upsample_nchw_kernel<2, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul, accumulate);
   TG_CUDA_LAUNCH_CHECK("upsample");
   return TG_OK;
 }

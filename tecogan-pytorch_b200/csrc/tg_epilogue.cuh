@@ -11,20 +11,13 @@ __device__ __forceinline__ void tg_epi_flow(const tg_conv_desc& d, int n, int y,
         24.f * tanhf(acc + __ldg(d.bias + ch));
 }
 
-// TG_EPI_OUT_NCHW_F32: out = conv_out(...) ; out += upsample_func(lr_curr) (tecogan_nets.py:144-145).
-// y already holds upsample_func(lr_curr) (tg_upsample_nchw_f32); fp32 add is commutative, so
-// (conv + bias) + up is the reference's value.
+// TG_EPI_OUT_NCHW_F32: out = conv_out(...) (tecogan_nets.py:144); the `+= upsample_func(lr_curr)`
+// of :145 is applied afterwards by tg_upsample_nchw_f32(accumulate=1): (conv + bias) + up.
 __device__ __forceinline__ void tg_epi_out(const tg_conv_desc& d, int n, int y, int x, int H,
-                                           int W, int ch, float acc, float y_prev) {
+                                           int W, int ch, float acc) {
   if (ch < d.cout_real)
     reinterpret_cast<float*>(d.y)[(((size_t)n * d.cout_real + ch) * H + y) * W + x] =
-        (acc + __ldg(d.bias + ch)) + y_prev;
-}
-__device__ __forceinline__ float tg_epi_out_prev(const tg_conv_desc& d, int n, int y, int x, int H,
-                                                 int W, int ch) {
-  return ch < d.cout_real
-             ? reinterpret_cast<const float*>(d.y)[(((size_t)n * d.cout_real + ch) * H + y) * W + x]
-             : 0.f;
+        acc + __ldg(d.bias + ch);
 }
 
 // TG_EPI_NHWC_F16 value: act(acc + bias) [+ residual]
@@ -53,7 +46,6 @@ __device__ __forceinline__ void tg_epilogue_store8(const tg_conv_desc& d, int n,
     for (int j = 0; j < 8; ++j) tg_epi_flow(d, n, oy, ox, OH, OW, c0 + j, a[j]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      tg_epi_out(d, n, oy, ox, OH, OW, c0 + j, a[j], tg_epi_out_prev(d, n, oy, ox, OH, OW, c0 + j));
+    for (int j = 0; j < 8; ++j) tg_epi_out(d, n, oy, ox, OH, OW, c0 + j, a[j]);
   }
 }

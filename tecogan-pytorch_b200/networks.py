@@ -152,9 +152,9 @@ class SRNet(nn.Module):
             a = c.get(('r', i, 2), blk.conv[2], L.CONV_3X3, L.ACT_NONE)(t, residual=a)
         for u in range(0, len(self.conv_up), 2):
             a = c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU)(a)
-        # out = upsample_func(lr_curr), then the output head accumulates conv_out + bias into it
-        out = ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out)
-        return c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)(a, y=out)
+        # out = conv_out(a) (pure-store epilogue), then out += upsample_func(lr_curr)
+        out = c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)(a, y=out)
+        return ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out, accumulate=True)
 
     def conv_layers(self, h, w):
         out = [(self.conv_in[0], h, w)]

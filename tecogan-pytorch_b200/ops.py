@@ -102,16 +102,13 @@ class PackedConv:
         return (n, self.cout_real, h, w), torch.float32
 
     def __call__(self, x, y=None, residual=None, impl=None, a_mode=None, max_ctas=0):
-        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None; EPI_OUT accumulates into y, which
-        the caller must have pre-filled)."""
+        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None)."""
         _req(x, torch.float16, 'conv input', 4)
         n, h, w, cin = x.shape
         if cin != self.cin:
             raise L.TecoganB200Error(f'conv input has {cin} channels, layer expects {self.cin}')
         shape, dtype = self.out_shape(n, h, w)
         if y is None:
-            if self.epilogue == L.EPI_OUT_NCHW_F32:
-                raise L.TecoganB200Error('EPI_OUT_NCHW_F32 accumulates into y: pass a pre-filled y')
             y = torch.empty(shape, dtype=dtype, device=x.device)
         else:
             _req(y, dtype, 'conv output')
@@ -259,15 +256,15 @@ def space_to_depth(x, scale, y=None):
     return y
 
 
-def upsample(x, scale, up_mode, out_hw=None, mul=1.0, y=None):
-    """mul * upsample_func(reflect_pad(x -> out_hw)); out_hw defaults to x's own size."""
+def upsample(x, scale, up_mode, out_hw=None, mul=1.0, y=None, accumulate=False):
+    """[y +] mul * upsample_func(reflect_pad(x -> out_hw)); out_hw defaults to x's own size."""
     _req(x, torch.float32, 'x', 4)
     n, c, hin, win = x.shape
     h, w = out_hw if out_hw is not None else (hin, win)
     if y is None:
         y = torch.empty((n, c, h * scale, w * scale), dtype=torch.float32, device=x.device)
     L.check(L.load().tg_upsample_nchw_f32(_ptr(x), _ptr(y), n, c, hin, win, h, w, scale, up_mode,
-                                          ctypes.c_float(mul), _stream()), 'tg_upsample')
+                                          ctypes.c_float(mul), int(accumulate), _stream()), 'tg_upsample')
     return y
 
 

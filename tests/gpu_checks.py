@@ -231,8 +231,8 @@ def check_conv_epilogues(impl='tcgen05'):
         b = rand(55, 3, lo=-0.1, hi=0.1)
         lr = rand(56, 1, 3, 6, 10)
         pc = ops.PackedConv(wt.to(DEV), b.to(DEV), L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
-        base = ops.upsample(lr.to(DEV), s, L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR)
-        y = pc(nhwc(x), y=base, impl=impl).cpu()
+        y = pc(nhwc(x), impl=impl)
+        y = ops.upsample(lr.to(DEV), s, L.UP_BICUBIC if mode == 'BD' else L.UP_BILINEAR, y=y, accumulate=True).cpu()
         up = K.bicubic_upsample(lr.numpy(), s) if mode == 'BD' else K.bilinear_upsample(lr.numpy(), s)
         ref = F.conv2d(f16(x), f16(wt), b, padding=1) + torch.from_numpy(up)
         out[f'out_{mode}{s}_rel'] = relmax(y.numpy(), ref.numpy())

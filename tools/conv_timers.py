@@ -55,13 +55,13 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'tapn':
+        for flags in ('0', '1', '2', '3'):
+            os.environ['TG_DBG_FLAGS'] = flags
+            run(f'conv_out flags={flags}', 64, 3, 536, 1280, 4, epilogue=L.EPI_OUT_NCHW_F32)
+        sys.exit(0)
     run('res 64->64 halo n4', 64, 64, 134, 320, 4)
     run('res 64->64 halo+residual n4', 64, 64, 134, 320, 4, residual=True)
-    run('res 64->64 tap n4', 64, 64, 134, 320, 4, a_mode=L.AMODE_TAP)
     run('convT 64->64 268x640 n4', 64, 64, 268, 640, 4, kind=L.CONVT_3X3_S2)
     run('conv_out 64->3 536x1280 n4', 64, 3, 536, 1280, 4, epilogue=L.EPI_OUT_NCHW_F32)
-    os.environ['TG_DBG_NBUF'] = '2'
-    run('conv_out NBUF=2', 64, 3, 536, 1280, 4, epilogue=L.EPI_OUT_NCHW_F32)
-    run('res 64->64 halo NBUF=2', 64, 64, 134, 320, 4)
-    del os.environ['TG_DBG_NBUF']
     run('fnet 256->256 16x40 n4', 256, 256, 16, 40, 4)

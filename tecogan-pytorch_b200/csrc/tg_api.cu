@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, device query.
 #include "tg_common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 static thread_local char g_err[512] = "";
@@ -10,6 +11,15 @@ void tg_set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool tg_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TECOGAN_B200_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 extern "C" {

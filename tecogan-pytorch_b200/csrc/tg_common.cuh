@@ -30,6 +30,34 @@ void tg_set_error(const char* fmt, ...);
 
 static inline int tg_ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// and begins with tg_pdl_wait(): the next kernel of the stream (or captured graph) is scheduled onto
+// SMs as the previous one drains and runs its prologue (barrier init, TMEM allocation, weight
+// loads) before blocking on the predecessor's completion -- launch latency and tail imbalance of
+// the ~48 dependent launches of a step overlap instead of adding up.  TECOGAN_B200_PDL=0 disables.
+bool tg_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void tg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void tg_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------- packed-weight geometry
 // One weight tile = [cout_pad rows][64 k] fp16, 128-byte rows, 128B swizzle:
 // byte offset of (row n, k) = n*128 + (((k>>3) ^ (n&7))<<4) + (k&7)*2.

@@ -14,6 +14,8 @@ namespace {
 // convT  : w[ci][co][ky][kx] -> tile (g per tg_group(TG_CONVT_3X3_S2, g)), same element map
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ packed,
                                     int kind, int cout, int cin, int cout_pad, int cin_pad) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int chunks = cin_pad / 64;
   const size_t total = (size_t)9 * chunks * cout_pad * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -38,6 +40,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
 // tap-major N layout for thin heads: tile per chunk [48 rows][64 k], row = tap*4 + co
 __global__ void pack_weights_tapn_kernel(const float* __restrict__ w, __half* __restrict__ packed,
                                          int cout, int cin, int cin_pad) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int chunks = cin_pad / 64;
   const size_t total = (size_t)chunks * TG_TAPN_ROWS * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -55,6 +59,8 @@ __global__ void pack_weights_tapn_kernel(const float* __restrict__ w, __half* __
 
 // ------------------------------------------------------------------ cross-check conv
 __global__ void conv_simt_kernel(tg_conv_desc d) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int chunks = d.cin / 64;
   const int n_acc = d.kind == TG_CONV_3X3 ? 1 : 4;
   const bool tapn = d.epilogue != TG_EPI_NHWC_F16;
@@ -122,8 +128,8 @@ static int pack_common(const float* w, int kind, int cout, int cin, void* packed
   const size_t total = (size_t)9 * cin_pad * cout_pad;
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
-  pack_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, kind, cout, cin,
-                                                             cout_pad, cin_pad);
+  tg_launch(pack_weights_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, w, (__half*)packed, kind, cout, cin,
+            cout_pad, cin_pad);
   TG_CUDA_LAUNCH_CHECK("pack_weights");
   return TG_OK;
 }
@@ -148,8 +154,8 @@ int tg_pack_conv3x3_weights_tapn(const float* w_oihw, int cout, int cin, void* p
   TG_REQUIRE(w_oihw && packed, TG_E_INVALID, "pack_weights_tapn: null pointer");
   TG_REQUIRE(cout >= 1 && cout <= 4 && cin > 0 && cin <= cin_pad && cin_pad % 64 == 0, TG_E_UNSUPPORTED,
              "pack_weights_tapn: cout=%d (<=4) cin=%d cin_pad=%d", cout, cin, cin_pad);
-  pack_weights_tapn_kernel<<<(cin_pad / 64) * 12, 256, 0, (cudaStream_t)stream>>>(
-      w_oihw, (__half*)packed, cout, cin, cin_pad);
+  tg_launch(pack_weights_tapn_kernel, dim3((cin_pad / 64) * 12), dim3(256), 0, (cudaStream_t)stream, w_oihw,
+            (__half*)packed, cout, cin, cin_pad);
   TG_CUDA_LAUNCH_CHECK("pack_weights_tapn");
   return TG_OK;
 }
@@ -164,7 +170,7 @@ int tg_conv_simt(const tg_conv_desc* d, void* stream) {
                        (d->epilogue != TG_EPI_NHWC_F16 ? 1 : d->cout / 8);
   size_t grid = (total + 127) / 128;
   if (grid > 148 * 64) grid = 148 * 64;
-  conv_simt_kernel<<<(int)grid, 128, 0, (cudaStream_t)stream>>>(*d);
+  tg_launch(conv_simt_kernel, dim3((unsigned)grid), dim3(128), 0, (cudaStream_t)stream, *d);
   TG_CUDA_LAUNCH_CHECK("conv_simt");
   return TG_OK;
 }

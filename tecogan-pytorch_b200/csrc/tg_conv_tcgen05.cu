@@ -272,6 +272,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Everything above (barrier init, TMEM allocation, bias) is independent of the previous kernel and
+  // may run while it drains (programmatic dependent launch); its output is only read below.
+  tg_pdl_wait();
+  tg_pdl_trigger();
   if (timing && threadIdx.x == 0) p.dbg[blockIdx.x * T_SLOTS + T_PROLOGUE] = clock64() - t_kernel0;
 
   const uint32_t smem_b = base + p.off_b;
@@ -341,7 +345,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       // descriptor templates: everything but the 14-bit start address is constant per kernel
       constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
       constexpr int kOrg = (KIND == TG_CONV_3X3) ? -1 : 0;
-      const uint64_t a_hi = make_sdesc(0, MODE == MODE_HALO ? (uint32_t)kBoxW * 128u : 1024u);
+      const uint64_t a_hi = make_sdesc(0, (MODE == MODE_HALO && !(p.dbg_flags & 8)) ? (uint32_t)kBoxW * 128u : 1024u);
       const uint64_t b_hi = make_sdesc(0, 1024u);
       const uint32_t btb16 = p.b_tile_bytes >> 4;
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
@@ -379,7 +383,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
                   const TgGroup gr = MODE == MODE_TAPN ? TgGroup{0, 0, 0, 0, 0} : tg_group(KIND, g);
                   // first MMA into an accumulator (per tile) overwrites, the rest accumulate
                   const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
-                  const uint32_t a16 = MODE == MODE_TAPN
+                  const uint32_t a16 = (MODE == MODE_TAPN || (p.dbg_flags & 4))   // flag 4: timing experiment only
                                            ? sa16
                                            : sa16 + (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
                   const uint32_t b16 = smem_b16 + (uint32_t)(g * p.chunks + c) * btb16;
@@ -777,15 +781,17 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t lerr = cudaSuccess;
   if (tapn) {
-    conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
+    lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
   } else if (d->kind == TG_CONV_3X3) {
-    if (p.halo) conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
-    else        conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
+    if (p.halo) lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
+    else        lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
   } else {
-    if (p.halo) conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
-    else        conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP><<<grid, kThreads, kSmemLimit, st>>>(map_a, p);
+    if (p.halo) lerr = tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
+    else        lerr = tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
   }
+  TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "conv_tcgen05: launch failed: %s", cudaGetErrorString(lerr));
   TG_CUDA_LAUNCH_CHECK("conv_tcgen05");
   return TG_OK;
 }

@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(128)
 warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                        const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
                        int w, int h8, int w8, int up_mode, int cpad) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   constexpr int LRW = 128 / S;
   constexpr int FW = LRW + 3;                 // LR columns x0-1 .. x0+LRW+1
   constexpr int FH = RY + 3;                  // LR rows    y0-1 .. y0+RY+1
@@ -144,6 +146,8 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
 // =====================================================================================
 __global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
                                   int w, int c8) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int ho = h / 2, wo = w / 2;
   const size_t total = (size_t)n * ho * wo * c8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -172,6 +176,8 @@ __global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict
 // out[2i] = .25*in[max(i-1,0)] + .75*in[i], out[2i+1] = .75*in[i] + .25*in[min(i+1,L-1)]
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
                                   int w, int c8) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int ho = 2 * h, wo = 2 * w;
   const size_t total = (size_t)n * ho * wo * c8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -214,6 +220,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 __global__ void pack_pair_kernel(const float* __restrict__ x1, const float* __restrict__ x2,
                                  uint4* __restrict__ y, int n, int c, int h, int w, int c8,
                                  int c_offset, int zero_fill) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const size_t hw = (size_t)h * w;
   const size_t total = (size_t)n * hw * c8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -241,6 +249,8 @@ __global__ void pack_pair_kernel(const float* __restrict__ x1, const float* __re
 
 __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, float* __restrict__ y, int n,
                                     int c, int h, int w, int cpad) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const size_t hw = (size_t)h * w;
   const size_t total = (size_t)n * c * hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -257,6 +267,8 @@ __global__ void nhwc_to_nchw_kernel(const __half* __restrict__ x, float* __restr
 // =====================================================================================
 __global__ void backward_warp_kernel(const float* __restrict__ x, const float* __restrict__ flow,
                                      float* __restrict__ y, int n, int c, int h, int w) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const size_t hw = (size_t)h * w;
   const size_t total = (size_t)n * hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -273,6 +285,8 @@ __global__ void backward_warp_kernel(const float* __restrict__ x, const float* _
 
 __global__ void space_to_depth_kernel(const float* __restrict__ x, float* __restrict__ y, int n,
                                       int c, int h, int w, int s) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const int oh = h / s, ow = w / s;
   const size_t total = (size_t)n * c * s * s * oh * ow;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -294,6 +308,8 @@ template <int S, int RY>
 __global__ void __launch_bounds__(128)
 upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int hin, int win, int h,
                      int w, int up_mode, float mul, int accumulate) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   constexpr int LRW = 128 / S;
   constexpr int FW = LRW + 3, FH = RY + 3;
   __shared__ float fsrc[FH * FW];
@@ -338,6 +354,8 @@ __device__ __forceinline__ uint32_t tg_q8(float v) {
 }
 __global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, int n, int c,
                                 int h, int w) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const size_t hw = (size_t)h * w;
   const size_t total = (size_t)n * hw;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -350,6 +368,8 @@ __global__ void to_uint8_kernel(const float* __restrict__ x, uint8_t* __restrict
 // c == 3, hw % 4 == 0: one thread = 4 pixels = three float4 loads -> 12 bytes = three u32 stores
 __global__ void to_uint8_c3x4_kernel(const float4* __restrict__ x, uint32_t* __restrict__ y, int n,
                                      size_t hw4) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
   const size_t total = (size_t)n * hw4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -401,11 +421,11 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   const size_t smem = (size_t)lrw * cpad * sizeof(__half);
   __half* o = (__half*)out;
   if (s == 4) {
-    if (lrflow) warp_s2d_concat_kernel<4, true, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<4, false, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) tg_launch(warp_s2d_concat_kernel<4, true, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        tg_launch(warp_s2d_concat_kernel<4, false, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   } else {
-    if (lrflow) warp_s2d_concat_kernel<2, true, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        warp_s2d_concat_kernel<2, false, RY><<<grid, 128, smem, st>>>(hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (lrflow) tg_launch(warp_s2d_concat_kernel<2, true, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    else        tg_launch(warp_s2d_concat_kernel<2, false, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
   }
   TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
   return TG_OK;
@@ -429,8 +449,7 @@ int tg_maxpool2x2_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, v
   TG_REQUIRE(n > 0 && h >= 2 && w >= 2 && c > 0 && c % 8 == 0, TG_E_INVALID,
              "maxpool2x2: bad shape n=%d h=%d w=%d c=%d", n, h, w, c);
   const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool2x2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)y, n, h, w, c / 8);
+  tg_launch(maxpool2x2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, n, h, w, c / 8);
   TG_CUDA_LAUNCH_CHECK("maxpool2x2");
   return TG_OK;
 }
@@ -440,8 +459,7 @@ int tg_upsample2x_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w,
   TG_REQUIRE(x && y, TG_E_INVALID, "upsample2x: null pointer");
   TG_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, TG_E_INVALID, "upsample2x: bad shape");
   const size_t total = (size_t)n * (2 * h) * (2 * w) * (c / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)y, n, h, w, c / 8);
+  tg_launch(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, n, h, w, c / 8);
   TG_CUDA_LAUNCH_CHECK("upsample2x");
   return TG_OK;
 }
@@ -452,8 +470,7 @@ int tg_pack_pair_nhwc_f16(const float* x1, const float* x2, void* y, int n, int 
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && cpad % 8 == 0 && 2 * c <= cpad, TG_E_INVALID,
              "pack_pair: bad shape");
   const size_t total = (size_t)n * h * w * (cpad / 8);
-  pack_pair_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      x1, x2, (uint4*)y, n, c, h, w, cpad / 8, 0, 1);
+  tg_launch(pack_pair_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x1, x2, (uint4*)y, n, c, h, w, cpad / 8, 0, 1);
   TG_CUDA_LAUNCH_CHECK("pack_pair");
   return TG_OK;
 }
@@ -467,8 +484,7 @@ int tg_nchw_f32_to_nhwc_f16(const float* x, void* y, int n, int c, int h, int w,
   // touches, which must not be shared with other sources (c_offset % 8 == 0).
   TG_REQUIRE(c_offset % 8 == 0, TG_E_UNSUPPORTED, "nchw_to_nhwc: c_offset must be a multiple of 8");
   const size_t total = (size_t)n * h * w * (cpad / 8);
-  pack_pair_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      x, nullptr, (uint4*)y, n, c, h, w, cpad / 8, c_offset, c_offset == 0 ? 1 : 0);
+  tg_launch(pack_pair_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, nullptr, (uint4*)y, n, c, h, w, cpad / 8, c_offset, c_offset == 0 ? 1 : 0);
   TG_CUDA_LAUNCH_CHECK("nchw_to_nhwc");
   return TG_OK;
 }
@@ -478,8 +494,7 @@ int tg_nhwc_f16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w,
   TG_REQUIRE(x && y, TG_E_INVALID, "nhwc_to_nchw: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && c <= cpad, TG_E_INVALID, "nhwc_to_nchw: bad shape");
   const size_t total = (size_t)n * c * h * w;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, y, n, c, h, w, cpad);
+  tg_launch(nhwc_to_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, y, n, c, h, w, cpad);
   TG_CUDA_LAUNCH_CHECK("nhwc_to_nchw");
   return TG_OK;
 }
@@ -489,7 +504,7 @@ int tg_backward_warp_nchw_f32(const float* x, const float* flow, float* y, int n
   TG_REQUIRE(x && flow && y, TG_E_INVALID, "backward_warp: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "backward_warp: bad shape");
   const size_t total = (size_t)n * h * w;
-  backward_warp_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, flow, y, n, c, h, w);
+  tg_launch(backward_warp_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, flow, y, n, c, h, w);
   TG_CUDA_LAUNCH_CHECK("backward_warp");
   return TG_OK;
 }
@@ -499,7 +514,7 @@ int tg_space_to_depth_nchw_f32(const float* x, float* y, int n, int c, int h, in
   TG_REQUIRE(x && y, TG_E_INVALID, "space_to_depth: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && s > 0 && h >= s && w >= s, TG_E_INVALID, "space_to_depth: bad shape");
   const size_t total = (size_t)n * c * s * s * (h / s) * (w / s);
-  space_to_depth_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w, s);
+  tg_launch(space_to_depth_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n, c, h, w, s);
   TG_CUDA_LAUNCH_CHECK("space_to_depth");
   return TG_OK;
 }
@@ -515,8 +530,8 @@ int tg_upsample_nchw_f32(const float* x, float* y, int n, int c, int hin, int wi
   TG_REQUIRE(h <= 65535 && (size_t)n * c <= 65535, TG_E_UNSUPPORTED, "upsample: grid too large");
   constexpr int RY = 4;
   dim3 grid(tg_ceil_div(w, 128 / s), tg_ceil_div(h, RY), n * c);
-  if (s == 4) upsample_nchw_kernel<4, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul, accumulate);
-  else        upsample_nchw_kernel<2, RY><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, hin, win, h, w, up_mode, mul, accumulate);
+  if (s == 4) tg_launch(upsample_nchw_kernel<4, RY>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, x, y, hin, win, h, w, up_mode, mul, accumulate);
+  else        tg_launch(upsample_nchw_kernel<2, RY>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, x, y, hin, win, h, w, up_mode, mul, accumulate);
   TG_CUDA_LAUNCH_CHECK("upsample");
   return TG_OK;
 }
@@ -526,10 +541,9 @@ int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int 
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, TG_E_INVALID, "float_to_uint8: bad shape");
   const size_t total = (size_t)n * h * w;
   if (c == 3 && ((size_t)h * w) % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 3) == 0)
-    to_uint8_c3x4_kernel<<<grid_for(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const float4*)x, (uint32_t*)y, n, (size_t)h * w / 4);
+    tg_launch(to_uint8_c3x4_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, (uint32_t*)y, n, (size_t)h * w / 4);
   else
-    to_uint8_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, c, h, w);
+    tg_launch(to_uint8_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n, c, h, w);
   TG_CUDA_LAUNCH_CHECK("float_to_uint8");
   return TG_OK;
 }

@@ -55,6 +55,11 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'align':
+        for flags in ('0', '4', '12'):
+            os.environ['TG_DBG_FLAGS'] = flags
+            run(f'res halo flags={flags} (4: no tap shift, 8: SBO=1024)', 64, 64, 134, 320, 4)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'tapn':
         for flags in ('0', '1', '2', '3'):
             os.environ['TG_DBG_FLAGS'] = flags

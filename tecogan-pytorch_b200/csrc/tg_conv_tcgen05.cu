@@ -272,10 +272,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
-  // Everything above (barrier init, TMEM allocation, bias) is independent of the previous kernel and
-  // may run while it drains (programmatic dependent launch); its output is only read below.
-  tg_pdl_wait();
-  tg_pdl_trigger();
   if (timing && threadIdx.x == 0) p.dbg[blockIdx.x * T_SLOTS + T_PROLOGUE] = clock64() - t_kernel0;
 
   const uint32_t smem_b = base + p.off_b;
@@ -283,14 +279,20 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   const unsigned char* wglob = reinterpret_cast<const unsigned char*>(d.weights);
   const int n_tiles_w = (MODE == MODE_TAPN ? 1 : 9) * p.chunks;
 
+  // Resident weights do not depend on the previous kernel: start their load, then join the
+  // programmatic-dependent-launch wait.  Everything up to here (barrier init, TMEM allocation, bias,
+  // weights) overlaps the predecessor's tail; its OUTPUT is only read after tg_pdl_wait().
+  if (warp == 0 && lane == 0 && p.b_resident) {
+    mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_tile_bytes);
+    for (int t = 0; t < n_tiles_w; ++t)
+      bulk_load(smem_b + t * p.b_tile_bytes, wglob + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, bar_b);
+  }
+  tg_pdl_wait();
+  tg_pdl_trigger();
+
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0) {
-      if (p.b_resident) {
-        mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_tile_bytes);
-        for (int t = 0; t < n_tiles_w; ++t)
-          bulk_load(smem_b + t * p.b_tile_bytes, wglob + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, bar_b);
-      }
       int stage = 0;
       uint32_t phase = 0;
       long long tw = 0;

@@ -15,7 +15,7 @@ namespace {
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ packed,
                                     int kind, int cout, int cin, int cout_pad, int cin_pad) {
   tg_pdl_wait();
-  tg_pdl_trigger();
+  // no early trigger: the weights this kernel writes are loaded by the next conv BEFORE its PDL wait
   const int chunks = cin_pad / 64;
   const size_t total = (size_t)9 * chunks * cout_pad * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
@@ -41,7 +41,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
 __global__ void pack_weights_tapn_kernel(const float* __restrict__ w, __half* __restrict__ packed,
                                          int cout, int cin, int cin_pad) {
   tg_pdl_wait();
-  tg_pdl_trigger();
+  // no early trigger: the weights this kernel writes are loaded by the next conv BEFORE its PDL wait
   const int chunks = cin_pad / 64;
   const size_t total = (size_t)chunks * TG_TAPN_ROWS * 64;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;

@@ -267,7 +267,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
-  for (int i = threadIdx.x; i < d.cout; i += kThreads) bias_s[i] = d.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -279,8 +278,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   const unsigned char* wglob = reinterpret_cast<const unsigned char*>(d.weights);
   const int n_tiles_w = (MODE == MODE_TAPN ? 1 : 9) * p.chunks;
 
-  // Resident weights do not depend on the previous kernel: start their load, then join the
-  // programmatic-dependent-launch wait.  Everything up to here (barrier init, TMEM allocation, bias,
+  // Resident weights do not depend on the previous kernel (they are static during graph replay; on
+  // the eager path tg_pack_* never triggers its dependents early and a bias copy separates it from
+  // the conv): start their load, then join the programmatic-dependent-launch wait.  Everything up to here (barrier init, TMEM allocation, bias,
   // weights) overlaps the predecessor's tail; its OUTPUT is only read after tg_pdl_wait().
   if (warp == 0 && lane == 0 && p.b_resident) {
     mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_tile_bytes);
@@ -289,6 +289,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   }
   tg_pdl_wait();
   tg_pdl_trigger();
+  // bias may have been written by the immediately preceding kernel (host-side refresh): read it
+  // only after the wait.  The epilogue warps that consume bias_s pass the barrier below first.
+  for (int i = threadIdx.x; i < d.cout; i += kThreads) bias_s[i] = d.bias[i];
+  __syncthreads();
 
   if (warp == 0) {
     // ============================================================ TMA producer

@@ -283,9 +283,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   // the conv): start their load, then join the programmatic-dependent-launch wait.  Everything up to here (barrier init, TMEM allocation, bias,
   // weights) overlaps the predecessor's tail; its OUTPUT is only read after tg_pdl_wait().
   if (warp == 0 && lane == 0 && p.b_resident) {
-    mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_tile_bytes);
+    // this CTA's 64-row slice of every weight tile (nb is fixed per CTA: gridDim.x % n_split == 0)
+    const uint32_t nb = blockIdx.x % (uint32_t)p.n_split;
+    mbar_expect_tx(bar_b, (uint32_t)n_tiles_w * p.b_stage_bytes);
     for (int t = 0; t < n_tiles_w; ++t)
-      bulk_load(smem_b + t * p.b_tile_bytes, wglob + (size_t)t * p.b_tile_bytes, p.b_tile_bytes, bar_b);
+      bulk_load(smem_b + t * p.b_stage_bytes, wglob + (size_t)t * p.b_tile_bytes + (size_t)nb * p.b_stage_bytes,
+                p.b_stage_bytes, bar_b);
   }
   tg_pdl_wait();
   tg_pdl_trigger();
@@ -353,7 +356,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       constexpr int kOrg = (KIND == TG_CONV_3X3) ? -1 : 0;
       const uint64_t a_hi = make_sdesc(0, (MODE == MODE_HALO && !(p.dbg_flags & 8)) ? (uint32_t)kBoxW * 128u : 1024u);
       const uint64_t b_hi = make_sdesc(0, 1024u);
-      const uint32_t btb16 = p.b_tile_bytes >> 4;
+      const uint32_t btb16 = p.b_stage_bytes >> 4;      // resident weight tiles are 64-row slices
       const uint32_t smem_b16 = (smem_b & 0x3FFFFu) >> 4;
       long long tw_tempty = 0, tw_full = 0, t_issue = 0;
       const long long t_mma0 = TG_T0();
@@ -691,7 +694,12 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
 
-  const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_tile_bytes;
+  // Output channels beyond 64 are split over CTAs (N = 64 per CTA): cout/64 x more CTAs on the
+  // low-resolution FNet layers, and each CTA only needs its own 64-row slice of every weight tile.
+  p.n_split = (!tapn && d->cout > 64) ? d->cout / 64 : 1;
+  p.bn = d->cout / p.n_split;
+  p.b_stage_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_stage_bytes;   // resident slice per CTA
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
   uint32_t staging = tapn ? 4u * kTapnEBytes : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
@@ -700,10 +708,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   const uint32_t halo_stage = (halo_bytes + 1023u) & ~1023u;
   uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
 
-  const bool can_resident_halo = d->cout <= 64 && fixed + b_total + 2u * halo_stage <= kSmemLimit;
-  // cout > 64 only occurs on the low-resolution FNet layers: few spatial tiles, so stream the
-  // weights and split N over CTAs instead of making every CTA load all of them
-  const bool can_resident_tap = d->cout <= 64 && fixed + b_total + 2u * kTapABytes <= kSmemLimit;
+  const bool can_resident_halo = fixed + b_total + 2u * halo_stage <= kSmemLimit;
+  const bool can_resident_tap = fixed + b_total + 2u * kTapABytes <= kSmemLimit;
   int mode = d->a_mode;
   if (tapn) mode = TG_AMODE_TAP;          // placeholder; thin heads always run MODE_TAPN below
   if (mode == TG_AMODE_AUTO) mode = can_resident_halo ? TG_AMODE_HALO : TG_AMODE_TAP;
@@ -711,11 +717,6 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
              "conv_tcgen05: halo mode needs the weights resident in smem (cin=%d cout=%d)", d->cin, d->cout);
   p.halo = mode == TG_AMODE_HALO;
   p.b_resident = p.halo ? 1 : (can_resident_tap ? 1 : 0);
-  // streamed weights: split the output channels over CTAs of 64 columns -> cout/64 x more CTAs on
-  // the low-resolution FNet layers, each streaming 1/(cout/64) of the weights
-  p.n_split = (!p.b_resident && d->cout > 64) ? d->cout / 64 : 1;
-  p.bn = d->cout / p.n_split;
-  p.b_stage_bytes = (uint32_t)p.bn * 128u;
   p.num_tiles *= p.n_split;
   p.idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   TG_REQUIRE(p.bn == 64 || (tapn && p.bn == TG_TAPN_ROWS), TG_E_UNSUPPORTED,
@@ -784,6 +785,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   if (rc != TG_OK) return rc;
   int grid = d->max_ctas > 0 ? d->max_ctas : sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
+  grid -= grid % p.n_split;             // every CTA keeps one fixed N slice (resident weights)
   // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;

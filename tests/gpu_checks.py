@@ -418,6 +418,7 @@ CHECKS = {
     'conv_tc_tap_256_128': lambda: check_conv('tcgen05', L.AMODE_TAP, cin=256, cout=128, h=33, w=80, n=1),
     'conv_tc_tap_64_128': lambda: check_conv('tcgen05', None, cin=64, cout=128, h=33, w=80, n=2),
     'conv_tc_nsplit_res': lambda: check_conv('tcgen05', None, cin=128, cout=128, h=17, w=20, act=L.ACT_NONE, residual=True),
+    'conv_tc_auto_128_256': lambda: check_conv('tcgen05', None, cin=128, cout=256, h=16, w=40),
     'conv_tc_auto_pad': lambda: check_conv('tcgen05', None, cin=64, cout=64, cin_real=51, cout_real=32, act=L.ACT_LRELU02),
     'epilogues_tc': lambda: check_conv_epilogues('tcgen05'),
     'conv_tc_vs_simt_tap_full': lambda: check_conv_vs_simt(L.AMODE_TAP),

@@ -118,15 +118,53 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
           v[sy] = __ldg(f1 + (size_t)sy * W);
         }
       }
+      if (C == 3) {
+        // two-phase gather: compute the 4 corner offsets of all S pixels, issue all 12*S loads,
+        // then combine -- 12*S independent loads in flight per thread hide the L2/DRAM latency
+        int o00[S], o01[S], o10[S], o11[S];
+        float ax[S], ay[S];
 #pragma unroll
-      for (int sy = 0; sy < S; ++sy) {
-        const float fx = (float)X + u[sy];
-        const float fy = (float)(y * S + sy) + v[sy];
-        // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
-        __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
-        for (int k = 0; k < C; ++k) {
-          const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
-          dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+        for (int sy = 0; sy < S; ++sy) {
+          float fx = (float)X + u[sy];
+          float fy = (float)(y * S + sy) + v[sy];
+          fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+          fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+          const float x0f = floorf(fx), y0f = floorf(fy);
+          const int xa = (int)x0f, ya = (int)y0f;
+          const int xb = min(xa + 1, W - 1), yb = min(ya + 1, H - 1);
+          ax[sy] = fx - x0f; ay[sy] = fy - y0f;
+          o00[sy] = ya * W + xa; o01[sy] = ya * W + xb; o10[sy] = yb * W + xa; o11[sy] = yb * W + xb;
+        }
+        float g[S][3][4];
+        const float* img = hr_prev + (size_t)n * 3 * H * W;
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float* plane = img + (size_t)k * H * W;
+            g[sy][k][0] = __ldg(plane + o00[sy]); g[sy][k][1] = __ldg(plane + o01[sy]);
+            g[sy][k][2] = __ldg(plane + o10[sy]); g[sy][k][3] = __ldg(plane + o11[sy]);
+          }
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy) {
+          // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
+          __half* dst = tile + lx * cpad + 3 + (sy * S + sx) * 3;
+          const float w00 = (1.f - ax[sy]) * (1.f - ay[sy]), w01 = ax[sy] * (1.f - ay[sy]);
+          const float w10 = (1.f - ax[sy]) * ay[sy], w11 = ax[sy] * ay[sy];
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            dst[k] = __float2half(g[sy][k][0] * w00 + g[sy][k][1] * w01 + g[sy][k][2] * w10 + g[sy][k][3] * w11);
+        }
+      } else {
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy) {
+          const float fx = (float)X + u[sy];
+          const float fy = (float)(y * S + sy) + v[sy];
+          __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
+          for (int k = 0; k < C; ++k) {
+            const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
+            dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+          }
         }
       }
     }

@@ -35,6 +35,7 @@ class ClipEngine:
             self.h2d = torch.cuda.Stream(device=dev)
             self.d2h = torch.cuda.Stream(device=dev)
             self.launches_per_step = None
+            self.stage = None
             if self.use_graph:
                 self._capture()
 
@@ -80,40 +81,45 @@ class ClipEngine:
 
     def run_clips(self, lr_host, out_host=None):
         """lr_host: pinned CPU tensor (or CUDA tensor) [n,t,c,h,w] fp32; returns a pinned uint8
-        tensor [t,n,H,W,c].  Per frame: n contiguous H2D copies (one per clip, no host-side
-        transpose), one graph replay, one D2H copy -- on three streams, so the copies overlap the
-        compute of neighbouring frames; one synchronisation at the end."""
+        tensor [t,n,H,W,c].  Three streams: H2D copies land in a 2-deep device staging ring (so the
+        copy of frame i+1 overlaps the compute of frame i -- lr[p] itself is still being read as
+        lr_prev), the main stream moves staging -> lr[p] (device-to-device, ~2 us) and replays the
+        step graph, and the D2H stream drains the uint8 frames; one synchronisation at the end."""
         t = lr_host.shape[1]
         if out_host is None:   # caching host allocator: cheap after the first call
             out_host = torch.empty((t, self.n, self.H, self.W, self.c), dtype=torch.uint8,
                                    pin_memory=True)
         with torch.cuda.device(self.device):
+            if self.stage is None:
+                self.stage = [torch.empty_like(self.lr[0]) for _ in range(2)]
             self.main.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.main):
                 self.reset()
-            in_ready = [None, None]
-            frame_done = [None, None]      # compute of parity p finished (u8[p] valid, lr[p] consumed)
+            staged = [None, None]          # H2D into stage[q] finished
+            consumed = [None, None]        # stage[q] copied into lr[] (free for the next H2D)
             out_copied = [None, None]      # D2H of u8[p] finished
             self.h2d.wait_stream(self.main)
             for i in range(t):
-                p = i & 1
+                p = q = i & 1
                 with torch.cuda.stream(self.h2d):
-                    # lr[p] was last READ by frame i-1 (as lr_prev); wait for that frame
-                    if frame_done[p ^ 1] is not None:
-                        self.h2d.wait_event(frame_done[p ^ 1])
+                    if consumed[q] is not None:
+                        self.h2d.wait_event(consumed[q])
                     for k in range(self.n):
-                        self.lr[p][k].copy_(lr_host[k, i], non_blocking=True)
-                    in_ready[p] = torch.cuda.Event()
-                    in_ready[p].record(self.h2d)
+                        self.stage[q][k].copy_(lr_host[k, i], non_blocking=True)
+                    staged[q] = torch.cuda.Event()
+                    staged[q].record(self.h2d)
                 with torch.cuda.stream(self.main):
-                    self.main.wait_event(in_ready[p])
+                    self.main.wait_event(staged[q])
+                    self.lr[p].copy_(self.stage[q], non_blocking=True)
+                    consumed[q] = torch.cuda.Event()
+                    consumed[q].record(self.main)
                     if out_copied[p] is not None:
                         self.main.wait_event(out_copied[p])    # u8[p] free to overwrite
                     self.run_frame(p)
-                    frame_done[p] = torch.cuda.Event()
-                    frame_done[p].record(self.main)
+                    done = torch.cuda.Event()
+                    done.record(self.main)
                 with torch.cuda.stream(self.d2h):
-                    self.d2h.wait_event(frame_done[p])
+                    self.d2h.wait_event(done)
                     out_host[i].copy_(self.u8[p], non_blocking=True)
                     out_copied[p] = torch.cuda.Event()
                     out_copied[p].record(self.d2h)

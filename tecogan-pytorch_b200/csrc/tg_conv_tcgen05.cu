@@ -365,6 +365,70 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       // queued in the tensor pipe, so the poll latencies (~100-200 cycles each) do not drain it.
       int buf = 0;
       uint32_t bphase = 0;
+      const bool pair_mode = MODE == MODE_HALO && p.chunks == 1 && p.n_stages >= 2 && p.n_buf >= 2 &&
+                             !(p.dbg_flags & 16);
+      if (pair_mode) {
+        // Two tiles are issued interleaved, MMA by MMA, into two TMEM accumulators.  Back-to-back
+        // MMAs that accumulate into the SAME accumulator serialise on its read-modify-write
+        // (measured ~77 cycles per 128x64x16 MMA); alternating between two independent
+        // accumulators lets the tensor pipe overlap them (the transposed conv, whose taps already
+        // spread over 4 accumulators, runs the same MMAs at ~48 cycles).
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+          const bool two = tile + (int)gridDim.x < p.num_tiles;
+          const int bufA = buf;
+          const uint32_t bphA = bphase;
+          const int bufB = (bufA + 1 == p.n_buf) ? 0 : bufA + 1;
+          const uint32_t bphB = (bufA + 1 == p.n_buf) ? (bphA ^ 1u) : bphA;
+          const int stA = stage;
+          const uint32_t phA = phase;
+          const int stB = (stA + 1 == p.n_stages) ? 0 : stA + 1;
+          const uint32_t phB = (stA + 1 == p.n_stages) ? (phA ^ 1u) : phA;
+          long long t0 = TG_T0();
+          mbar_wait(bar_tempty + 8 * bufA, bphA ^ 1, 4);
+          if (two) mbar_wait(bar_tempty + 8 * bufB, bphB ^ 1, 4);
+          TG_ACC(tw_tempty, t0);
+          t0 = TG_T0();
+          mbar_wait(bar_full + 8 * stA, phA, 5);
+          if (two) mbar_wait(bar_full + 8 * stB, phB, 5);
+          TG_ACC(tw_full, t0);
+          tc_fence_after();
+          const uint32_t saA = ((smem_stage0 + stA * p.stage_bytes) & 0x3FFFFu) >> 4;
+          const uint32_t saB = ((smem_stage0 + stB * p.stage_bytes) & 0x3FFFFu) >> 4;
+          const uint32_t dA = tmem_base + bufA * acc_stride, dB = tmem_base + bufB * acc_stride;
+          const long long t_i0 = TG_T0();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int g = 0; g < 9; ++g) {
+              const TgGroup gr = tg_group(KIND, g);
+              const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
+              const uint32_t off = (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
+              const uint32_t b16 = smem_b16 + (uint32_t)g * btb16;
+              const uint32_t dcol = (uint32_t)gr.acc * (uint32_t)p.bn;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t accf = (first_of_acc && k == 0) ? 0u : 1u;
+                umma_f16(dA + dcol, a_hi | (uint64_t)(saA + off + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc, accf);
+                if (two)
+                  umma_f16(dB + dcol, a_hi | (uint64_t)(saB + off + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc, accf);
+              }
+            }
+            umma_commit(bar_empty + 8 * stA);
+            if (two) umma_commit(bar_empty + 8 * stB);
+            umma_commit(bar_tfull + 8 * bufA);
+            if (two) umma_commit(bar_tfull + 8 * bufB);
+          }
+          __syncwarp();
+          TG_ACC(t_issue, t_i0);
+          if (two) {
+            stage = (stB + 1 == p.n_stages) ? 0 : stB + 1;
+            phase = (stB + 1 == p.n_stages) ? (phB ^ 1u) : phB;
+            buf = (bufB + 1 == p.n_buf) ? 0 : bufB + 1;
+            bphase = (bufB + 1 == p.n_buf) ? (bphB ^ 1u) : bphB;
+          } else {
+            it -= 1;      // only one tile issued in this round (it is advanced by 2 below)
+          }
+        }
+      } else {
       if (blockIdx.x < p.num_tiles) {
         mbar_wait(bar_tempty, 1, 4);              // fresh barrier: passes immediately
         mbar_wait(bar_full, 0, 5);
@@ -458,6 +522,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         }
         buf = nbuf; bphase = nbphase;
       }
+      }   // !pair_mode
       if (timing && lane == 0) {
         unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
         o[T_MMA_WAIT_TEMPTY] = tw_tempty; o[T_MMA_WAIT_FULL] = tw_full; o[T_MMA_ISSUE] = t_issue;

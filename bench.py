@@ -118,8 +118,15 @@ def cpu_reference_fps(steps, warmup, threads=None):
     """Reference CPU path, 1 clip-frame per step (a bounded sample of the 4-clip step)."""
     import torch
     from oracle import frnet_torchref as R
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use the host cores this
+    # process may run on (affinity mask, capped at 64: oversubscribing oneDNN's OpenMP pool stalls)
+    if threads is None and torch.get_num_threads() == 1:
+        try:
+            threads = min(64, len(os.sched_getaffinity(0)))
+        except Exception:
+            threads = None
+    if threads:
+        torch.set_num_threads(threads)
     p = make_params()
     g = torch.Generator().manual_seed(0)
     lr_curr = torch.rand(1, *LR, generator=g)

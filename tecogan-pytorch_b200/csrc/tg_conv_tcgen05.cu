@@ -541,13 +541,6 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;   // row of the tile = TMEM lane
     const int ty = r >> 3, tx = r & 7;
-    // Scattered per-thread row stores cost one LSU wavefront per 32 bytes (~1000 cycles per 128x64
-    // unit): fine when the MMAs of a tile take longer (plain 64->64 conv), but the transposed conv
-    // (4 units per tile) and the residual conv (row loads + row stores) become LSU-bound.  Those
-    // transpose through a warp-private smem scratch and store whole rows per instruction.
-    const bool coalesce = MODE != MODE_TAPN && (KIND == TG_CONVT_3X3_S2 || d.residual != nullptr) &&
-                          !(p.dbg_flags & 32);
-    uint8_t* wscratch = sm + p.off_staging + (uint32_t)(warp - 4) * 4096u;
     const uint32_t acc_stride = p.acc_stride;
     long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
     const long long t_epi0 = TG_T0();
@@ -616,37 +609,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
                 o[j] = __floats2half2_rn(a0, a1);
               }
             }
-            if (!coalesce) {
-              if (inb) {
-                st_global_256(orow + pc * 4, ov[0], ov[1]);
-                st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
-              }
-            } else {
-              // stage this thread's half row in the warp's private 4 KB scratch (128B rows, XOR swizzle)
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                *reinterpret_cast<uint4*>(wscratch + lane * 128 + (((pc * 4 + i) ^ (lane & 7)) << 4)) = ov[i];
+            if (inb) {
+              st_global_256(orow + pc * 4, ov[0], ov[1]);
+              st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
             }
-          }
-          if (coalesce) {
-            // warp-private transpose: each store instruction now writes 4 whole 128-byte pixel rows
-            // (lane L: 16-byte chunk L%8 of pixel L/8 + 4j) instead of 32 scattered 32-byte pieces
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int row = (lane >> 3) + 4 * j, ch = lane & 7;
-              const uint4 val = *reinterpret_cast<const uint4*>(wscratch + row * 128 + ((ch ^ (row & 7)) << 4));
-              const int rr = q * 32 + row;
-              const int ppy = tc.y0 + (rr >> 3), ppx = tc.x0 + (rr & 7);
-              if (ppy < d.h && ppx < d.w) {
-                int oy2 = ppy, ox2 = ppx;
-                if (KIND == TG_CONVT_3X3_S2) { oy2 = 2 * ppy + (acc >> 1); ox2 = 2 * ppx + (acc & 1); }
-                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y) +
-                                                      (((size_t)tc.n * OH + oy2) * OW + ox2) * d.cout + tc.nb * p.bn);
-                dst[ch] = val;
-              }
-            }
-            __syncwarp();
           }
         }
         TG_ACC(te_compute, t_s);
@@ -800,7 +766,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_stage_bytes = (uint32_t)p.bn * 128u;
   const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_stage_bytes;   // resident slice per CTA
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
-  uint32_t staging = tapn ? 4u * kTapnEBytes : 8u * 4096u;   // NHWC: 4 KB transpose scratch per epilogue warp
+  uint32_t staging = tapn ? 4u * kTapnEBytes : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;

@@ -56,9 +56,9 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
 
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'pair':
-        for flags in ('0', '32'):
+        for flags in ('0', '16'):
             os.environ['TG_DBG_FLAGS'] = flags
-            run(f'res halo flags={flags} (32: no coalesced stores)', 64, 64, 134, 320, 4)
+            run(f'res halo flags={flags} (16: no pair interleave)', 64, 64, 134, 320, 4)
             run(f'res halo+res flags={flags}', 64, 64, 134, 320, 4, residual=True)
             run(f'convT flags={flags}', 64, 64, 268, 640, 4, kind=L.CONVT_3X3_S2)
         sys.exit(0)

@@ -395,6 +395,67 @@ def check_engine_matches_eager(n=2, t=5, h=24, w=40):
     return {}
 
 
+# =============================================================================== size-independent properties
+def check_properties_fullsize(n=2, h=134, w=320):
+    """BASELINE-size properties that need no oracle run: (1) the fused warp kernel with zero flow
+    is an exact space_to_depth of hr_prev (bit exact after the fp16 rounding), (2) conv linearity
+    conv(a+b) - conv(b) = conv(a) - bias-free part, within fp16 rounding, (3) the transposed conv's
+    four parity outputs interleave without overlap or holes (every output pixel written exactly
+    once: a poisoned buffer comes back fully overwritten), (4) step() is deterministic."""
+    out = {}
+    hr = rand(80, n, 3, 4 * h, 4 * w)
+    lr = rand(81, n, 3, h, w)
+    zero = torch.zeros(n, 2, 4 * h, 4 * w)
+    x = ops.warp_s2d_concat_hrflow(hr.to(DEV), zero.to(DEV), lr.to(DEV), 4)
+    ref = torch.cat([lr, torch.from_numpy(K.space_to_depth(hr.numpy(), 4))], 1)
+    assert torch.equal(from_nhwc(x, 51), f16(ref)), 'zero-flow warp must be an exact space_to_depth'
+    # linearity on a 64->64 conv without activation
+    wt = rand(82, 64, 64, 3, 3, lo=-0.05, hi=0.05)
+    pc = ops.PackedConv(wt.to(DEV), torch.zeros(64, device=DEV), L.CONV_3X3, L.ACT_NONE)
+    a = nhwc(rand(83, 1, 64, h, w, lo=-1, hi=1), 64)
+    b = nhwc(rand(84, 1, 64, h, w, lo=-1, hi=1), 64)
+    ya, yb, yab = pc(a).float(), pc(b).float(), pc((a.float() + b.float()).half()).float()
+    lin = float((yab - ya - yb).abs().max() / yab.abs().max())
+    out['linearity_rel'] = lin
+    assert lin <= 4e-3, out           # three fp16 roundings of O(1) values
+    # transposed conv coverage
+    pt = ops.PackedConv(rand(85, 64, 64, 3, 3, lo=-0.05, hi=0.05).to(DEV), torch.ones(64, device=DEV),
+                        L.CONVT_3X3_S2, L.ACT_RELU)
+    y = torch.full((1, 2 * h, 2 * w, 64), float('nan'), dtype=torch.float16, device=DEV)
+    pt(a, y=y)
+    assert not bool(torch.isnan(y).any()), 'transposed conv left output pixels unwritten'
+    # determinism of the whole step
+    net, p = _net(17, 4, 'BD', 1.0, nb=2)
+    args = (rand(86, n, 3, h, w).to(DEV), rand(87, n, 3, h, w).to(DEV), rand(88, n, 3, 4 * h, 4 * w).to(DEV))
+    assert torch.equal(net.step(*args), net.step(*args)), 'step() must be deterministic'
+    return out
+
+
+def check_ragged_sizes():
+    """Sizes that are not multiples of the 16x8 tile, of 8 (FNet reflect pad) or of the 14x6 thin-head
+    tile: step() against the CPU oracle."""
+    out = {}
+    for (hh, ww) in ((17, 23), (9, 8), (31, 50)):
+        net, p = _net(18, 4, 'BD', 1.5, nb=2)
+        a, b, c = rand(90, 1, 3, hh, ww), rand(91, 1, 3, hh, ww), rand(92, 1, 3, 4 * hh, 4 * ww)
+        got = net.step(a.to(DEV), b.to(DEV), c.to(DEV)).cpu().numpy()
+        ref = O.frnet_step(p, a, b, c, 4, 'BD').numpy()
+        out[f'{hh}x{ww}'] = rell2(got, ref)
+        assert out[f'{hh}x{ww}'] <= 1e-3, out
+    return out
+
+
+def check_bi2_fullsize(h=268, w=640):
+    """BASELINE config 5 shape (2x BI, LR 3x268x640): one step against the CPU oracle."""
+    net, p = _net(19, 2, 'BI', 1.0)
+    a, b, c = rand(93, 1, 3, h, w), rand(94, 1, 3, h, w), rand(95, 1, 3, 2 * h, 2 * w)
+    got = net.step(a.to(DEV), b.to(DEV), c.to(DEV)).cpu().numpy()
+    ref = O.frnet_step(p, a, b, c, 2, 'BI').numpy()
+    out = {'rel_l2': rell2(got, ref), 'rel_max': relmax(got, ref)}
+    assert out['rel_l2'] <= 1e-3, out
+    return out
+
+
 CHECKS = {
     'warp_hrflow_s4': lambda: check_warp_hrflow(4),
     'warp_hrflow_s2': lambda: check_warp_hrflow(2, h=9, w=70),
@@ -433,6 +494,9 @@ CHECKS = {
     'forward_sequence_golden': check_forward_sequence_golden,
     'batch_consistency': check_batch_consistency,
     'engine_matches_eager': check_engine_matches_eager,
+    'properties_fullsize': check_properties_fullsize,
+    'ragged_sizes': check_ragged_sizes,
+    'bi2_fullsize': check_bi2_fullsize,
     'step_vs_oracle_fullsize': check_step_vs_oracle_fullsize,
     'step_vs_oracle_fullsize_g15': lambda: check_step_vs_oracle_fullsize(gain=1.5, frames=2),
 }

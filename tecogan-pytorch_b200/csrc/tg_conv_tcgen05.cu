@@ -136,6 +136,12 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const u
                "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+// 256-bit read-only streaming load (sm_100+): half the LSU wavefronts of two 128-bit loads
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
@@ -428,6 +434,41 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             it -= 1;      // only one tile issued in this round (it is advanced by 2 below)
           }
         }
+      } else if (MODE == MODE_TAPN && p.chunks == 1 && p.n_stages >= 4 && p.n_buf >= 4 && !(p.dbg_flags & 16)) {
+        // Thin heads: a tile is only 4 MMAs, so the fixed poll / commit latencies of the issue loop
+        // dominate; issue up to four tiles per round (4 accumulators, 4 smem stages).
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += 4 * gridDim.x) {
+          int cnt = 0, bufs[4], sts[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (tile + j * (int)gridDim.x < p.num_tiles) {
+              bufs[j] = buf; sts[j] = stage;
+              mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
+              mbar_wait(bar_full + 8 * stage, phase, 5);
+              if (++buf == p.n_buf) { buf = 0; bphase ^= 1u; }
+              if (++stage == p.n_stages) { stage = 0; phase ^= 1u; }
+              cnt = j + 1;
+            }
+          }
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < cnt) {
+                const uint32_t sa16 = ((smem_stage0 + sts[j] * p.stage_bytes) & 0x3FFFFu) >> 4;
+                const uint32_t dcol = tmem_base + bufs[j] * acc_stride;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(dcol, a_hi | (uint64_t)(sa16 + 2u * k), b_hi | (uint64_t)(smem_b16 + 2u * k), p.idesc,
+                           k == 0 ? 0u : 1u);
+                umma_commit(bar_empty + 8 * sts[j]);
+                umma_commit(bar_tfull + 8 * bufs[j]);
+              }
+            }
+          }
+          __syncwarp();
+          it += cnt;
+        }
       } else {
       if (blockIdx.x < p.num_tiles) {
         mbar_wait(bar_tempty, 1, 4);              // fresh barrier: passes immediately
@@ -563,7 +604,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             reinterpret_cast<const __half*>(d.residual) +
             (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) res[i] = __ldg(rp + i);
+        for (int i = 0; i < 8; i += 2) ld_global_256(rp + i, res[i], res[i + 1]);
       }
       mbar_wait(bar_tfull + 8 * buf, bphase, 7);
       TG_ACC(te_tfull, t_s);

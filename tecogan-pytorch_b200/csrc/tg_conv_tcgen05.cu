@@ -30,7 +30,13 @@
 namespace {
 
 constexpr int TH = 16, TW = 8;
-constexpr int kThreads = 384;
+// 4 control warps (TMA producer, MMA issuer, TMEM allocator, spare) + G epilogue groups of 4 warps.
+// The transposed conv (4 accumulators per tile) and the thin heads (tiny MMA work per tile) are
+// epilogue-bound: they run 4 groups (640 threads, <= 102 registers); the plain convs 2 groups.
+__host__ __device__ constexpr int epi_groups(int kind, int mode) {
+  return (mode == 2 /*MODE_TAPN*/ || kind == TG_CONVT_3X3_S2) ? 4 : 2;
+}
+__host__ __device__ constexpr int conv_threads(int kind, int mode) { return 128 + 128 * epi_groups(kind, mode); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kHeaderBytes = 2048;   // barriers + tmem ptr (first 1 KB) + bias (second 1 KB)
@@ -236,7 +242,7 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
 
 // ------------------------------------------------------------------ the kernel
 template <int KIND, int MODE, bool TIMING>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(conv_threads(KIND, MODE), 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -300,7 +306,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   tg_pdl_trigger();
   // bias may have been written by the immediately preceding kernel (host-side refresh): read it
   // only after the wait.  The epilogue warps that consume bias_s pass the barrier below first.
-  for (int i = threadIdx.x; i < d.cout; i += kThreads) bias_s[i] = d.bias[i];
+  for (int i = threadIdx.x; i < d.cout; i += conv_threads(KIND, MODE)) bias_s[i] = d.bias[i];
   __syncthreads();
 
   if (warp == 0) {
@@ -572,11 +578,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue
-    // Two groups of 4 warps; group g owns TMEM accumulator buffer g and therefore every second
-    // tile of this CTA, so one group's TMEM->regs->smem->TMA-store chain overlaps the other
-    // group's and both overlap the MMAs.  Warp q of a group reads TMEM lanes [32q, 32q+32) =
-    // tile rows, all bn columns.  Each group has two 16 KB staging buffers (ring): the TMA store
-    // of one (accumulator, 64-channel chunk) unit drains while the next unit is being written.
+    // G groups of 4 warps take the tiles of this CTA round-robin (tile it -> group it % G, TMEM buffer
+    // it % n_buf), so one group's TMEM -> registers -> global chain overlaps the other groups' and
+    // all overlap the MMAs.  Warp q of a group reads TMEM lanes [32q, 32q+32) = tile rows, all bn
+    // columns.
     const int group = (warp - 4) >> 2;
     const int gtid = threadIdx.x - 128 - group * 128;   // 0..127 inside the group
     const int q = warp & 3;        // TMEM lane quarter this warp may access
@@ -586,7 +591,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
     long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
     const long long t_epi0 = TG_T0();
     int it = group;
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += 2 * gridDim.x, it += 2) {
+    constexpr int G = epi_groups(KIND, MODE);
+    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x, it += G) {
       const int buf = it % p.n_buf;
       const uint32_t bphase = (uint32_t)(it / p.n_buf) & 1u;
       const TileCoord tc = tile_coord(p, tile);
@@ -598,7 +604,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       // operands that come from global memory are fetched BEFORE waiting for the accumulator so
       // their latency hides behind the MMAs of this tile
       uint4 res[8];
-      const bool has_res = (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
+      // the residual input exists only for the plain conv (validated on the host)
+      constexpr bool kCanRes = KIND == TG_CONV_3X3 && MODE != MODE_TAPN;
+      const bool has_res = kCanRes && (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(
             reinterpret_cast<const __half*>(d.residual) +
@@ -668,7 +676,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it >> 1) & 1)) * kTapnEBytes);
+        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it / G) & 1)) * kTapnEBytes);
         if (!(p.dbg_flags & 2))
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
@@ -807,7 +815,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_stage_bytes = (uint32_t)p.bn * 128u;
   const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_stage_bytes;   // resident slice per CTA
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
-  uint32_t staging = tapn ? 4u * kTapnEBytes : 0u;
+  // TAPN: epi_groups x 2 exchange buffers
+  uint32_t staging = tapn ? 2u * epi_groups(TG_CONV_3X3, MODE_TAPN) * kTapnEBytes : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
@@ -900,18 +909,18 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t lerr = cudaSuccess;
   if (tapn) {
-    lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, true>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p)
-                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, false>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
+    lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAPN)), kSmemLimit, st, map_a, p)
+                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, false>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAPN)), kSmemLimit, st, map_a, p);
   } else if (d->kind == TG_CONV_3X3) {
-    if (p.halo) lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, true>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p)
-                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, false>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
-    else        lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, true>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p)
-                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, false>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
+    if (p.halo) lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_HALO)), kSmemLimit, st, map_a, p)
+                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, false>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_HALO)), kSmemLimit, st, map_a, p);
+    else        lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAP)), kSmemLimit, st, map_a, p)
+                 : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, false>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAP)), kSmemLimit, st, map_a, p);
   } else {
-    if (p.halo) lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO, true>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p)
-                 : tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO, false>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
-    else        lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP, true>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p)
-                 : tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP, false>, dim3(grid), dim3(kThreads), kSmemLimit, st, map_a, p);
+    if (p.halo) lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO, true>, dim3(grid), dim3(conv_threads(TG_CONVT_3X3_S2, MODE_HALO)), kSmemLimit, st, map_a, p)
+                 : tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_HALO, false>, dim3(grid), dim3(conv_threads(TG_CONVT_3X3_S2, MODE_HALO)), kSmemLimit, st, map_a, p);
+    else        lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP, true>, dim3(grid), dim3(conv_threads(TG_CONVT_3X3_S2, MODE_TAP)), kSmemLimit, st, map_a, p)
+                 : tg_launch(conv_tcgen05_kernel<TG_CONVT_3X3_S2, MODE_TAP, false>, dim3(grid), dim3(conv_threads(TG_CONVT_3X3_S2, MODE_TAP)), kSmemLimit, st, map_a, p);
   }
   TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "conv_tcgen05: launch failed: %s", cudaGetErrorString(lerr));
   TG_CUDA_LAUNCH_CHECK("conv_tcgen05");

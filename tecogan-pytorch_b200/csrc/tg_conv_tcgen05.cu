@@ -263,7 +263,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 16 * kMaxStages + 136);
   float* bias_s = reinterpret_cast<float*>(sm + 1024);
 
-  const int epi_warps_active = 4;   // the 4 warps of the epilogue group that owns the buffer
+  // warps that release an accumulator buffer: the 4 warps of the group that owns the tile (for the
+  // transposed conv two groups share every tile, two parity accumulators each -> 8 warps)
+  const int epi_warps_active = KIND == TG_CONVT_3X3_S2 ? 8 : 4;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&map_a);
   if (warp == 1 && lane == 0) {
@@ -591,8 +593,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
     long long te_store_wait = 0, te_tfull = 0, te_compute = 0, te_store = 0;
     const long long t_epi0 = TG_T0();
     int it = group;
+    // A TMEM buffer must always be drained by the same group(s) (parity waits may not run two
+    // phases ahead): TG tile-level groups with n_buf % TG == 0.  The transposed conv has only two
+    // buffers, so its 4 groups work as 2 pairs -- both groups of a pair take every tile of the pair,
+    // group 2j handles parity accumulators 0,1 and group 2j+1 accumulators 2,3.
     constexpr int G = epi_groups(KIND, MODE);
-    for (int tile = blockIdx.x + group * gridDim.x; tile < p.num_tiles; tile += G * gridDim.x, it += G) {
+    constexpr bool kSplitAcc = KIND == TG_CONVT_3X3_S2;
+    constexpr int TG = kSplitAcc ? G / 2 : G;
+    const int tgroup = kSplitAcc ? (group >> 1) : group;
+    const int acc_lo = kSplitAcc ? 2 * (group & 1) : 0;
+    const int acc_hi = kSplitAcc ? acc_lo + 2 : p.n_acc;
+    it = tgroup;
+    for (int tile = blockIdx.x + tgroup * gridDim.x; tile < p.num_tiles; tile += TG * gridDim.x, it += TG) {
       const int buf = it % p.n_buf;
       const uint32_t bphase = (uint32_t)(it / p.n_buf) & 1u;
       const TileCoord tc = tile_coord(p, tile);
@@ -622,7 +634,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         // Each thread owns one output pixel = 64 channels = one contiguous 128-byte NHWC row: it
         // goes straight from registers to global memory (8 x 16-byte stores complete the line),
         // so the epilogue costs no shared-memory bandwidth -- the MMA operand reads need all of it.
-        for (int acc = 0; acc < p.n_acc; ++acc) {
+        for (int acc = acc_lo; acc < acc_hi; ++acc) {
           int oy = py, ox = px, OW = d.w, OH = d.h;
           if (KIND == TG_CONVT_3X3_S2) { oy = 2 * py + (acc >> 1); ox = 2 * px + (acc & 1); OW = 2 * d.w; OH = 2 * d.h; }
           uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y) +
@@ -632,7 +644,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             uint32_t v[32];
             tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + pc * 32 + ((uint32_t)(q * 32) << 16), v);
             tmem_ld_wait();
-            if (acc == p.n_acc - 1 && pc == 1) {
+            if (acc == acc_hi - 1 && pc == 1) {
               // all TMEM reads of this warp for this buffer are done -> hand it back to the MMA
               tc_fence_before();
               __syncwarp();
@@ -676,7 +688,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it / G) & 1)) * kTapnEBytes);
+        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it / TG) & 1)) * kTapnEBytes);
         if (!(p.dbg_flags & 2))
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)

@@ -688,7 +688,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)(group * 2 + ((it / TG) & 1)) * kTapnEBytes);
+        float4* E = reinterpret_cast<float4*>(sm + p.off_staging + (uint32_t)group * kTapnEBytes);
         if (!(p.dbg_flags & 2))
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap)
@@ -710,6 +710,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             else tg_epi_out(d, tc.n, py, px, d.h, d.w, ch, av[ch]);
           }
         }
+        // one exchange buffer per group (smem goes to TMA stages instead: the thin heads are bound
+        // by bytes in flight): everyone must be done reading before the next tile overwrites it
+        named_bar_sync(1 + group, 128);
         TG_ACC(te_compute, t_s);
       }
     }
@@ -827,8 +830,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.b_stage_bytes = (uint32_t)p.bn * 128u;
   const uint32_t b_total = (tapn ? 1u : 9u) * p.chunks * p.b_stage_bytes;   // resident slice per CTA
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
-  // TAPN: epi_groups x 2 exchange buffers
-  uint32_t staging = tapn ? 2u * epi_groups(TG_CONV_3X3, MODE_TAPN) * kTapnEBytes : 0u;
+  // TAPN: one exchange buffer per epilogue group
+  uint32_t staging = tapn ? (uint32_t)epi_groups(TG_CONV_3X3, MODE_TAPN) * kTapnEBytes : 0u;
   const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
   const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;

@@ -204,7 +204,11 @@ def time_kernels(dev, pk):
     out['roofline'] = {
         'kernel': 'conv_tcgen05_kernel<conv3x3, halo> (SRNet resblock conv 64->64, 4 frames/launch)',
         'bound': 'tensor', 'achieved': flops / t_conv / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
-        'frac': flops / t_conv / 1e12 / pk['tflops_burst'], 'traffic': None,
+        'frac': flops / t_conv / 1e12 / pk['tflops_burst'],
+        # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
+        # (profiles/ncu_conv_r1q.md, launch 1): 22.09 MB read (the fp16 input once) + 0.006 MB
+        # written inside the measured window (the 22 MB output stays in the 126 MB L2)
+        'traffic': 22.09152e6 + 0.006144e6, 'traffic_src': 'profiles/ncu_conv_r1q.md',
         'us_per_launch': t_conv * 1e6, 'flop_per_launch': flops,
         'peak_src': pk['src'] + ' burst (kernel timed alone)',
         'how': f'{reps} launches in one CUDA graph, {nbuf} rotating in/out pairs (440 MB > L2), CUDA events'}
@@ -229,7 +233,9 @@ def time_kernels(dev, pk):
         out['roofline_warp' if variant == 'hrflow' else 'roofline_warp_fused_lrflow'] = {
             'kernel': f'warp_s2d_concat_kernel<4,{variant}> (4 frames/launch)', 'bound': 'hbm',
             'achieved': alg / t / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': alg / t / 1e9 / pk['hbm_gbs'],
-            'traffic': None, 'us_per_launch': t * 1e6, 'algorithmic_bytes_per_launch': alg,
+            # one `ncu --set full` capture of the LR-flow variant (profiles/ncu_warp_r1q.md)
+            'traffic': (36.013312e6 + 0.192256e6) if variant == 'lrflow' else None,
+            'us_per_launch': t * 1e6, 'algorithmic_bytes_per_launch': alg,
             'bytes_actually_moved_per_launch': moved, 'moved_gbs': moved / t / 1e9,
             'peak_src': pk['src'], 'how': f'{reps} launches in one CUDA graph, {nb2} rotating buffer sets > L2'}
     return out

@@ -161,7 +161,55 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_eager_gpu(args, rank):
+    """Context comparator, NOT part of the contract: the reference's operator sequence
+    (oracle/frnet_torchref.py = the F.conv2d / grid_sample / interpolate calls the reference makes)
+    executed by PyTorch's CUDA library kernels (cuDNN) on the same B200, same 4-clip step, timed with
+    CUDA events.  Answers "what does the stock reference get on this GPU" (BASELINE.md section 5)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import frnet_torchref as R
+    dev = torch.device('cuda', 0)
+    torch.backends.cudnn.benchmark = True                      # codes/main.py:216
+    g = torch.Generator().manual_seed(0)
+    n = CLIPS_PER_GPU
+    base = [torch.rand(n, *LR, generator=g), torch.rand(n, *LR, generator=g),
+            torch.rand(n, LR[0], SCALE * LR[1], SCALE * LR[2], generator=g)]
+    out = {}
+    for name, dtype, tf32, cl in (('fp32', torch.float32, False, False), ('tf32', torch.float32, True, False),
+                                  ('fp16_channels_last', torch.float16, True, True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        p = {k: v.to(dev, dtype) for k, v in make_params().items()}
+        lr_curr, lr_prev, hr_prev = (t.to(dev, dtype) for t in base)
+        if cl:
+            lr_curr, lr_prev, hr_prev = (t.contiguous(memory_format=torch.channels_last)
+                                         for t in (lr_curr, lr_prev, hr_prev))
+        with torch.no_grad():
+            for _ in range(max(args.warmup, 3)):
+                hr_prev = R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                hr_prev = R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        out[name] = {'ms_per_step': ms, 'frames_per_s': n * 1e3 / ms}
+    print(json.dumps({'impl': 'eager-gpu', 'metric': 'hr_frames_per_sec_4xBD_3x134x320', 'unit': 'frames/s',
+                      'clips_per_step': n, 'steps': args.steps, 'device': torch.cuda.get_device_name(0),
+                      'note': 'reference operator sequence on PyTorch CUDA library kernels (cuDNN), no uint8/H2D',
+                      'results': out}), flush=True)
+
+
 # =============================================================================== our arm
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_chain_kernel launch (ncu --set full), or None
+CHAIN_DRAM_TRAFFIC = None
+CHAIN_DRAM_TRAFFIC_SRC = None
+
+
 def _time_graph(fn, nbuf, reps, torch):
     """Average device time of one fn(i) launch: `reps` launches over `nbuf` rotating buffer sets are
     captured in a CUDA graph (so the number is the kernel, not the Python launch rate) and the
@@ -212,6 +260,31 @@ def time_kernels(dev, pk):
         'us_per_launch': t_conv * 1e6, 'flop_per_launch': flops,
         'peak_src': pk['src'] + ' burst (kernel timed alone)',
         'how': f'{reps} launches in one CUDA graph, {nbuf} rotating in/out pairs (440 MB > L2), CUDA events'}
+    out['roofline_conv_single'] = out['roofline']
+    # ---- dominant kernel of the step: conv_in + 10 residual blocks as ONE persistent launch
+    if ops.chain_enabled():
+        nl = 21
+        pcs = [ops.PackedConv(torch.randn(64, 64, 3, 3, device=dev) * 0.04, torch.zeros(64, device=dev), L.CONV_3X3,
+                              L.ACT_RELU if (i == 0 or i % 2 == 1) else L.ACT_NONE) for i in range(nl)]
+        specs = [(pcs[0], 0, 1, None)]
+        for b in range(10):
+            specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
+        chain = ops.ConvChain(specs)
+        nb3 = 3                                  # 3 x (22 MB in + 2 x 22 MB work) = 198 MB > 126 MB L2
+        sets = [[xs[i], ys[i], torch.empty_like(xs[i])] for i in range(nb3)]
+        creps = 12
+        t_chain = _time_graph(lambda i: chain(sets[i]), nb3, creps, torch)
+        cflops = flops * nl
+        out['roofline'] = {
+            'kernel': 'conv_chain_kernel (SRNet conv_in + 10 residual blocks = 21 convs 64->64 in one persistent '
+                      'launch, 4 frames/launch)',
+            'bound': 'tensor', 'achieved': cflops / t_chain / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
+            'frac': cflops / t_chain / 1e12 / pk['tflops_burst'],
+            'traffic': CHAIN_DRAM_TRAFFIC, 'traffic_src': CHAIN_DRAM_TRAFFIC_SRC,
+            'us_per_launch': t_chain * 1e6, 'us_per_layer': t_chain * 1e6 / nl, 'flop_per_launch': cflops,
+            'peak_src': pk['src'] + ' burst (kernel timed alone)',
+            'how': f'{creps} launches in one CUDA graph, {nb3} rotating buffer sets (198 MB > L2), CUDA events'}
+        del sets
     del xs, ys
     # ---- fused warp + space_to_depth + concat, HR flow given (BASELINE.md byte formula)
     H, W = SCALE * h, SCALE * w
@@ -368,7 +441,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'eager-gpu'])
     ap.add_argument('--profile-only', action='store_true',
                     help='run only the device-resident step loop (for ncu captures); prints nothing')
     args = ap.parse_args()
@@ -377,6 +450,8 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if args.impl == 'reference':
         return run_reference(args, rank)
+    if args.impl == 'eager-gpu':
+        return run_eager_gpu(args, rank)
     run_ours(args, rank, world, local_rank)
 
 

@@ -48,8 +48,8 @@ def fnet(p, x1, x2):
 
 def warp(x, flow):
     n, c, h, w = x.shape
-    gx = torch.linspace(-1.0, 1.0, w).view(1, 1, 1, w).expand(n, -1, h, -1)
-    gy = torch.linspace(-1.0, 1.0, h).view(1, 1, h, 1).expand(n, -1, -1, w)
+    gx = torch.linspace(-1.0, 1.0, w, device=x.device, dtype=x.dtype).view(1, 1, 1, w).expand(n, -1, h, -1)
+    gy = torch.linspace(-1.0, 1.0, h, device=x.device, dtype=x.dtype).view(1, 1, h, 1).expand(n, -1, -1, w)
     g = torch.cat([gx + flow[:, 0:1] / ((w - 1.0) / 2.0), gy + flow[:, 1:2] / ((h - 1.0) / 2.0)], 1)
     return F.grid_sample(x, g.permute(0, 2, 3, 1), mode='bilinear', padding_mode='border',
                          align_corners=True)

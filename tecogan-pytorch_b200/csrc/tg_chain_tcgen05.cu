@@ -1,0 +1,603 @@
+// A chain of 64->64 3x3 convolutions (SRNet conv_in + residual blocks) as ONE persistent,
+// warp-specialised tcgen05 launch for sm_100a -- the layer loop lives inside the kernel.
+//
+//   tiles   : 16x8 output pixels (M = 128), static assignment tile = cta + k*grid for every layer
+//   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 3 stages; the nine
+//             taps are nine shifted UMMA-descriptor views of the box (see tg_conv_tcgen05.cu)
+//   B       : the layer's 73.7 KB of packed weights resident in smem, DOUBLE buffered: layer l+1's
+//             weights stream in while layer l computes (the buffer is released by a tcgen05.commit
+//             behind the last MMA of layer l-1)
+//   D       : one 64-column fp32 accumulator per tile, 8 tiles in flight in TMEM.  (Measured: the
+//             tensor pipe spends ~39 cycles per 128x64x16 MMA plus the time the epilogue needs to
+//             read the accumulator back -- TMEM reads run at 64 B/cycle and do not overlap the
+//             MMAs -- so the accumulator is NOT split into partial sums: that doubles the reads.)
+//   layers  : a tile of layer l needs the tiles of layer l-1 under its halo.  Epilogue groups
+//             publish `flags[tile] = epoch*32 + l + 1` (release, gpu scope) after their stores; a
+//             checker warp polls the <= 9 flags of up to three upcoming tiles per round (27 lanes)
+//             ahead of the TMA producer and hands it an in-order "verified" counter.  No launch,
+//             pipeline fill/drain, weight reload bubble or grid barrier between layers.
+//   roles   : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 dependency
+//             checker, warps 4..11 two epilogue groups alternating tiles.
+//
+// Replaces the 21 nn.Conv2d launches of SRNet.conv_in / ResidualBlock (tecogan_nets.py:92-100,
+// 111-116, 139-141) per step.
+#include <cuda.h>
+
+#include <cstdlib>
+#include <mutex>
+
+#include "tg_common.cuh"
+#include "tg_epilogue.cuh"
+#include "tg_tcgen05.cuh"
+
+#ifndef TG_CHAIN_EXP
+#define TG_CHAIN_EXP 0   // non-zero values are timing experiments (wrong results); never shipped
+#endif
+
+namespace {
+
+constexpr int TH = 16, TW = 8, BOXW = TW + 2, BOXH = TH + 2;
+constexpr int kThreads = 384;
+constexpr int kMaxMaps = 4;
+constexpr int kStages = 3;
+constexpr int kBufs = 8;                               // tiles in flight in TMEM (8 x 64 columns)
+constexpr uint32_t kAccStride = 64;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTapWBytes = 64 * 128;              // one tap: [64 cout rows][64 cin] fp16
+constexpr uint32_t kWBytes = 9 * kTapWBytes;           // 73,728 per layer
+constexpr uint32_t kHaloBytes = BOXW * BOXH * 128;     // 23,040
+constexpr uint32_t kStageBytes = (kHaloBytes + 1023u) & ~1023u;
+constexpr uint32_t kOffBias = 1024;                    // [layers][64] fp32
+constexpr uint32_t kOffW = kOffBias + TG_CHAIN_MAX_LAYERS * 256;
+constexpr uint32_t kOffStage = kOffW + 2 * kWBytes;
+constexpr uint32_t kSmemBytes = 1024 /*align slack*/ + kOffStage + kStages * kStageBytes;
+static_assert(kOffW % 1024 == 0 && kOffStage % 1024 == 0, "swizzle atoms need 1024B alignment");
+static_assert(kSmemBytes <= 232448, "227 KB opt-in shared memory limit");
+constexpr int kSyncFlags = 32;                         // uint32 index of the first tile flag
+
+struct ChainLayerDev {
+  const unsigned char* w;
+  const float* bias;
+  const __half* res;
+  __half* y;
+  int map, act;
+};
+struct ChainParams {
+  CUtensorMap maps[kMaxMaps];
+  ChainLayerDev layers[TG_CHAIN_MAX_LAYERS];
+  uint32_t* sync;                  // [0] epoch, [1] finished CTAs, [kSyncFlags + tile] progress
+  int n_layers, n, h, w, tiles_x, tiles_y, num_tiles;
+  uint32_t idesc;
+  unsigned long long* dbg;         // optional per-CTA timers (same slots as tg_conv_tcgen05)
+};
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_cta_shared(uint32_t saddr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// generic-proxy global writes <-> async-proxy (TMA) global reads
+__device__ __forceinline__ void fence_proxy_async_global() {
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+// 256-bit load served by L2 (strong, gpu scope): the data was written by another SM during this
+// kernel, so neither the L1 nor the non-coherent path may be used
+__device__ __forceinline__ void ld_global_256_l2(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr)
+               : "memory");
+}
+
+enum { CT_PROD_FLAGS = 0, CT_PROD_EMPTY, CT_MMA_TOTAL, CT_MMA_WAIT, CT_EPI_TFULL, CT_EPI_TOTAL, CT_KERNEL, CT_TILES,
+       CT_SLOTS = 16 };
+
+template <bool TIMING>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_chain_kernel(const __grid_constant__ ChainParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  constexpr bool timing = TIMING;
+  const long long t_kernel0 = timing ? clock64() : 0;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = base;                 // [kStages]
+  const uint32_t bar_empty = base + 32;           // [kStages]
+  const uint32_t bar_tfull = base + 64;           // [kBufs]
+  const uint32_t bar_tempty = base + 128;         // [kBufs]
+  const uint32_t bar_wfull = base + 192;          // [2] weights of the layer landed
+  const uint32_t bar_wfree = base + 208;          // [2] every MMA that read the buffer retired
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 224);
+  volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 228);
+  const uint32_t deps_ok_addr = base + 232;       // tiles (in this CTA's sequence) whose dependencies are verified
+  float* bias_s = reinterpret_cast<float*>(sm + kOffBias);
+  const uint32_t smem_w0 = base + kOffW;
+  const uint32_t smem_stage0 = base + kOffStage;
+
+  const int G = (int)gridDim.x, b = (int)blockIdx.x;
+  const int L = cp.n_layers;
+  const int n_my = (cp.num_tiles - 1 - b) / G + 1;      // grid <= num_tiles (host)
+  const int total = L * n_my;
+  const int per_img = cp.tiles_x * cp.tiles_y;
+  uint32_t* flags = cp.sync + kSyncFlags;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&cp.maps[i]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int i = 0; i < kBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 1); }
+    mbar_init(base + 240, 1);            // scratch barrier of the timing experiments
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // Weights are static across the step (packed at module init / refresh, never by the predecessor
+  // kernel): the first two layers' weights are requested before joining the PDL wait.
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < 2 && l < L; ++l) {
+      mbar_expect_tx(bar_wfull + 8 * l, kWBytes);
+      for (int t = 0; t < 9; ++t)
+        bulk_load(smem_w0 + l * kWBytes + t * kTapWBytes, cp.layers[l].w + (size_t)t * kTapWBytes, kTapWBytes,
+                  bar_wfull + 8 * l);
+    }
+  }
+  tg_pdl_wait();
+  tg_pdl_trigger();
+  for (int i = threadIdx.x; i < L * 64; i += kThreads) bias_s[i] = cp.layers[i >> 6].bias[i & 63];
+  if (threadIdx.x == 0) {
+    *epoch_s = ld_acquire_gpu(cp.sync);
+    *reinterpret_cast<volatile uint32_t*>(sm + 232) = (uint32_t)n_my;   // layer 0 has no dependencies
+  }
+  __syncthreads();
+  const uint32_t fbase = (*epoch_s) << 5;              // flags of this launch: fbase + layers done
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const int kpre = n_my - 1 < 4 ? n_my - 1 : 4;       // tile index at which layer l+1's weights are requested
+    long long tw_flags = 0, tw_empty = 0;
+    for (int l = 0; l < L; ++l) {
+      const CUtensorMap* map = &cp.maps[cp.layers[l].map];
+      for (int k = 0; k < n_my; ++k) {
+        const int tile = b + k * G;
+        const int n = tile / per_img;
+        const int r = tile - n * per_img;
+        const int ty = r / cp.tiles_x, tx = r - ty * cp.tiles_x;
+        if (l > 0) {
+          // the dependency checker (warp 3) has verified the halo tiles of every tile up to *deps_ok
+          const long long t0 = timing ? clock64() : 0;
+          const uint32_t seq = (uint32_t)(l * n_my + k);
+          if (lane == 0 && ld_acquire_cta_shared(deps_ok_addr) <= seq) {
+            const long long s0 = clock64();
+            while (ld_acquire_cta_shared(deps_ok_addr) <= seq) {
+              __nanosleep(32);                          // do not hammer shared memory: the MMA operands need it
+              if (clock64() - s0 > 3000000000LL) {
+                if (b < 2) printf("tg_conv_chain: dependency timeout block=%d layer=%d tile=%d\n", b, l, tile);
+                __trap();
+              }
+            }
+          }
+          __syncwarp();
+          if (timing) tw_flags += clock64() - t0;
+        }
+        if (lane == 0) {
+          if (l > 0) fence_proxy_async_global();
+          if (k == kpre && l >= 1 && l + 1 < L) {
+            // layer l+1's weights replace layer l-1's: wait until its last MMA has retired
+            mbar_wait(bar_wfree + 8 * ((l + 1) & 1), (uint32_t)((l - 1) >> 1) & 1u, 8);
+            mbar_expect_tx(bar_wfull + 8 * ((l + 1) & 1), kWBytes);
+            for (int t = 0; t < 9; ++t)
+              bulk_load(smem_w0 + ((l + 1) & 1) * kWBytes + t * kTapWBytes,
+                        cp.layers[l + 1].w + (size_t)t * kTapWBytes, kTapWBytes, bar_wfull + 8 * ((l + 1) & 1));
+          }
+          const long long t0 = timing ? clock64() : 0;
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+          if (timing) tw_empty += clock64() - t0;
+          mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
+          tma_load_4d(smem_stage0 + stage * kStageBytes, map, bar_full + 8 * stage, 0, tx * TW - 1, ty * TH - 1, n);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    if (timing && lane == 0) {
+      cp.dbg[b * CT_SLOTS + CT_PROD_FLAGS] = tw_flags;
+      cp.dbg[b * CT_SLOTS + CT_PROD_EMPTY] = tw_empty;
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    int stage = 0, buf = 0, l = 0, k = 0;
+    uint32_t phase = 0, bphase = 0;
+    const uint64_t a_hi = make_sdesc(0, (uint32_t)BOXW * 128u);   // 8-row groups = consecutive tile rows
+    const uint64_t b_hi = make_sdesc(0, 1024u);
+    const long long t_mma0 = timing ? clock64() : 0;
+    long long tw = 0;
+    mbar_wait(bar_wfull, 0, 3);
+    mbar_wait(bar_tempty, 1, 4);                 // fresh barrier: passes immediately
+    mbar_wait(bar_full, 0, 5);
+    tc_fence_after();
+    for (int g = 0; g < total; ++g) {
+      const bool last_k = k == n_my - 1;
+      const bool has_next = g + 1 < total;
+      const int nstage = (stage + 1 == kStages) ? 0 : stage + 1;
+      const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
+      const int nbuf = (buf + 1 == kBufs) ? 0 : buf + 1;
+      const uint32_t nbphase = (buf + 1 == kBufs) ? (bphase ^ 1u) : bphase;
+      const uint32_t sa16 = ((smem_stage0 + stage * kStageBytes) & 0x3FFFFu) >> 4;
+      const uint32_t wb16 = ((smem_w0 + (uint32_t)(l & 1) * kWBytes) & 0x3FFFFu) >> 4;
+      const uint32_t d0 = tmem_base + (uint32_t)buf * kAccStride;
+      bool next_ready = false;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int i = (part == 0 ? 0 : 28); i < (part == 0 ? 28 : 36); ++i) {
+            const int tap = i >> 2, kk = i & 3;
+            const uint32_t off = (uint32_t)((tap / 3) * BOXW + tap % 3) * 8u;   // (dy+1, dx+1) pixels, 128 B each
+#if TG_CHAIN_EXP == 6      /* timing experiment: only 18 of the 36 MMAs */
+            if (i >= 18) continue;
+#endif
+            umma_f16(d0, a_hi | (uint64_t)(sa16 + off + 2u * kk),
+                     b_hi | (uint64_t)(wb16 + (uint32_t)tap * (kTapWBytes >> 4) + 2u * kk), cp.idesc, i >= 1 ? 1u : 0u);
+#if TG_CHAIN_EXP == 5      /* timing experiment: every MMA twice into the SAME accumulator */
+            umma_f16(d0, a_hi | (uint64_t)(sa16 + off + 2u * kk),
+                     b_hi | (uint64_t)(wb16 + (uint32_t)tap * (kTapWBytes >> 4) + 2u * kk), cp.idesc, 1u);
+#endif
+#if TG_CHAIN_EXP == 2      /* timing experiment: a (dummy) commit after every tap */
+            if (kk == 3) umma_commit(base + 240);
+#endif
+          }
+          if (part == 1) {
+            umma_commit(bar_empty + 8 * stage);
+            umma_commit(bar_tfull + 8 * buf);
+            if (last_k) umma_commit(bar_wfree + 8 * (l & 1));
+          }
+        }
+        __syncwarp();
+        if (part == 0 && has_next) {
+          // look ahead while 28 MMAs are queued in the tensor pipe -- but never BLOCK before this
+          // tile is committed: the next tile may (transitively) depend on this one through the flags
+          uint32_t r = mbar_try_wait(bar_tempty + 8 * nbuf, nbphase ^ 1);
+          if (last_k) r &= mbar_try_wait(bar_wfull + 8 * ((l + 1) & 1), (uint32_t)((l + 1) >> 1) & 1u);
+          r &= mbar_try_wait(bar_full + 8 * nstage, nphase);
+          next_ready = __all_sync(0xFFFFFFFFu, r != 0);
+#if TG_CHAIN_EXP != 3     /* 3 = timing experiment: no tcgen05.fence::after_thread_sync in the loop */
+          if (next_ready) tc_fence_after();
+#endif
+        }
+      }
+      if (has_next && !next_ready) {
+        const long long t0 = timing ? clock64() : 0;
+        mbar_wait(bar_tempty + 8 * nbuf, nbphase ^ 1, 4);
+        if (last_k) mbar_wait(bar_wfull + 8 * ((l + 1) & 1), (uint32_t)((l + 1) >> 1) & 1u, 3);
+        mbar_wait(bar_full + 8 * nstage, nphase, 5);
+        if (timing) tw += clock64() - t0;
+        tc_fence_after();
+      }
+      stage = nstage; phase = nphase; buf = nbuf; bphase = nbphase;
+      if (last_k) { k = 0; ++l; } else { ++k; }
+    }
+    if (timing && lane == 0) {
+      cp.dbg[b * CT_SLOTS + CT_MMA_TOTAL] = clock64() - t_mma0;
+      cp.dbg[b * CT_SLOTS + CT_MMA_WAIT] = tw;
+      cp.dbg[b * CT_SLOTS + CT_TILES] = total;
+    }
+  } else if (warp == 3) {
+    // ============================================================ dependency checker
+    // Runs ahead of the TMA producer over a sliding window of 9 upcoming tiles of this CTA's
+    // sequence: tile q is watched by slot ((q - n_my) / 3) % 3 of the nine lanes (q - n_my) % 3,
+    // one lane per tile under its halo, polling that tile's progress flag (relaxed loads whose L2
+    // round trips overlap, one acquire fence per publication).  The in-order prefix of verified tiles is published
+    // through a shared-memory counter and the window slides on.
+    constexpr int R = 3, W = 3 * R;
+    const int sub = lane / 9, nbr = lane - sub * 9;
+    int q[R];
+    const uint32_t* f[R];
+    uint32_t need[R];
+    bool ok[R];
+    auto setup = [&](int rr) {
+      f[rr] = nullptr;
+      need[rr] = 0;
+      if (sub < 3 && q[rr] < total) {
+        const int l = q[rr] / n_my, k = q[rr] - l * n_my;
+        const int tile = b + k * G;
+        const int n = tile / per_img;
+        const int r = tile - n * per_img;
+        const int ty = r / cp.tiles_x, tx = r - ty * cp.tiles_x;
+        const int yy = ty + nbr / 3 - 1, xx = tx + nbr % 3 - 1;
+        if (yy >= 0 && yy < cp.tiles_y && xx >= 0 && xx < cp.tiles_x) {
+          f[rr] = flags + (size_t)n * per_img + yy * cp.tiles_x + xx;
+          need[rr] = fbase + (uint32_t)l;               // flag >= need  <=>  layer l-1 of that tile is published
+        }
+      }
+      ok[rr] = f[rr] == nullptr;
+    };
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) { q[rr] = n_my + rr * 3 + (sub < 3 ? sub : 0); setup(rr); }
+    int head = n_my;                                    // first tile of the sequence not yet verified
+    long long t_s = clock64();
+    while (head < total) {
+      uint32_t v[R], m[R];
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) v[rr] = ok[rr] ? 0u : ld_relaxed_gpu(f[rr]);   // independent: latencies overlap
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) {
+        if (!ok[rr]) ok[rr] = (int)(v[rr] - need[rr]) >= 0;
+        m[rr] = __ballot_sync(0xFFFFFFFFu, ok[rr]);
+      }
+      int p = 0;
+      while (p < W && head + p < total) {
+        const int rel = head + p - n_my;
+        const int slot = (rel / 3) % R, sb = rel % 3;
+        const uint32_t mm = slot == 0 ? m[0] : (slot == 1 ? m[1] : m[2]);
+        if (((mm >> (9 * sb)) & 0x1FFu) != 0x1FFu) break;
+        ++p;
+      }
+      if (p > 0) {
+        fence_acq_rel_gpu();                            // relaxed polls + fence = acquire (every lane)
+        __syncwarp();                                   // the other lanes' acquires happen-before the publication
+        if (lane == 0) st_release_cta_shared(deps_ok_addr, (uint32_t)(head + p));
+        head += p;
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+          if (q[rr] < head) { q[rr] += W; setup(rr); }
+        t_s = clock64();
+      } else if (clock64() - t_s > 3000000000LL) {
+        if (b < 2 && lane == 0) printf("tg_conv_chain: flag timeout block=%d seq=%d of %d\n", b, head, total);
+        __trap();
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue (2 groups alternate tiles)
+    const int grp = (warp - 4) >> 2;
+    const int gtid = threadIdx.x - 128 - grp * 128;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // tile row = TMEM lane
+    const int ry = r >> 3, rx = r & 7;
+    const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
+    long long te_tfull = 0;
+    const long long t_epi0 = timing ? clock64() : 0;
+    for (int g = grp; g < total; g += 2) {
+      const int l = g / n_my, k = g - l * n_my;
+      const int buf = g & (kBufs - 1);
+      const uint32_t bphase = (uint32_t)(g / kBufs) & 1u;
+      const int tile = b + k * G;
+      const int n = tile / per_img;
+      const int rr = tile - n * per_img;
+      const int ty = rr / cp.tiles_x, tx = rr - ty * cp.tiles_x;
+      const int py = ty * TH + ry, px = tx * TW + rx;
+      const bool inb = py < cp.h && px < cp.w;
+      const ChainLayerDev& ly = cp.layers[l];
+      const size_t pix = ((size_t)n * cp.h + py) * cp.w + px;
+      const float slope = tg_act_slope(ly.act);
+      uint4 res[8];
+      const bool has_res = ly.res != nullptr && inb;
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(ly.res + pix * 64);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) ld_global_256_l2(rp + i, res[i], res[i + 1]);
+      }
+      const long long t0 = timing ? clock64() : 0;
+      mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+      if (timing) te_tfull += clock64() - t0;
+      tc_fence_after();
+      uint4* orow = reinterpret_cast<uint4*>(ly.y + pix * 64);
+      const uint32_t tad = tmem_base + (uint32_t)buf * kAccStride + lane_bits;
+#pragma unroll
+      for (int pc = 0; pc < 2; ++pc) {
+        uint32_t v[32];
+#if TG_CHAIN_EXP == 1   /* timing experiment: no TMEM read-back (wrong results) */
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0;
+#else
+        tmem_ld32(tad + pc * 32, v);
+        tmem_ld_wait();
+#endif
+        if (pc == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        }
+        const float4* bias4 = reinterpret_cast<const float4*>(bias_s + l * 64 + pc * 32);
+        uint4 ov[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __half2* o = reinterpret_cast<__half2*>(&ov[i]);
+          const __half2* rh = reinterpret_cast<const __half2*>(&res[pc * 4 + i]);
+          const float4 b0 = bias4[i * 2], b1 = bias4[i * 2 + 1];
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = i * 8 + j * 2;
+            float a0 = __uint_as_float(v[c]) + bb[j * 2];
+            float a1 = __uint_as_float(v[c + 1]) + bb[j * 2 + 1];
+            a0 = fmaxf(a0, a0 * slope);
+            a1 = fmaxf(a1, a1 * slope);
+            if (has_res) {
+              const float2 rf = __half22float2(rh[j]);
+              a0 += rf.x; a1 += rf.y;
+            }
+            o[j] = __floats2half2_rn(a0, a1);
+          }
+        }
+        if (inb) {
+          st_global_256(orow + pc * 4, ov[0], ov[1]);
+          st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
+        }
+      }
+      if (l + 1 < L) {
+        // Publish the tile.  bar.sync orders the 128 threads' stores before thread 0 (CTA scope);
+        // its gpu-scope fence + release store is cumulative over them (the grid-barrier pattern:
+        // __syncthreads(); if (tid == 0) { __threadfence(); flag = 1; }).  One fence per tile, not
+        // one per thread: the fence has to wait for the stores to reach L2 and the group cannot
+        // take its next tile before it returns -- 128 of them made the epilogue the bottleneck.
+        // The consumers order the async proxy (TMA) behind their acquire with fence.proxy.async.
+        named_bar_sync(1 + grp, 128);
+        if (gtid == 0) {
+          fence_acq_rel_gpu();
+          st_release_gpu(flags + tile, fbase + (uint32_t)l + 1u);
+        }
+      }
+    }
+    if (timing && gtid == 0 && grp == 0) {
+      cp.dbg[b * CT_SLOTS + CT_EPI_TFULL] = te_tfull;
+      cp.dbg[b * CT_SLOTS + CT_EPI_TOTAL] = clock64() - t_epi0;
+    }
+  }
+
+  // ------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (threadIdx.x == 0) {
+    // last CTA out advances the epoch: the flags of this launch can never satisfy a later one
+    __threadfence();
+    const uint32_t done = atomicAdd(cp.sync + 1, 1u);
+    if (done == (uint32_t)G - 1u) {
+      atomicExch(cp.sync + 1, 0u);
+      __threadfence();
+      atomicExch(cp.sync, (*epoch_s) + 1u);
+    }
+    if (timing) cp.dbg[b * CT_SLOTS + CT_KERNEL] = clock64() - t_kernel0;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn chain_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace
+
+extern unsigned long long* tg_conv_timer_buffer();
+
+extern "C" {
+
+size_t tg_conv_chain_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h <= 0 || w <= 0) return 0;
+  const size_t tiles = (size_t)tg_ceil_div(w, TW) * tg_ceil_div(h, TH) * n;
+  return (kSyncFlags + tiles) * sizeof(uint32_t);
+}
+
+int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int h, int w, void* sync_ws,
+                          int max_ctas, void* stream) {
+  TG_REQUIRE(layers != nullptr && sync_ws != nullptr, TG_E_INVALID, "conv_chain: null pointer");
+  TG_REQUIRE(n_layers >= 1 && n_layers <= TG_CHAIN_MAX_LAYERS, TG_E_UNSUPPORTED,
+             "conv_chain: n_layers=%d (1..%d)", n_layers, TG_CHAIN_MAX_LAYERS);
+  TG_REQUIRE(n > 0 && h > 0 && w > 0, TG_E_INVALID, "conv_chain: bad size n=%d h=%d w=%d", n, h, w);
+  TG_REQUIRE(((uintptr_t)sync_ws & 15) == 0, TG_E_INVALID, "conv_chain: sync_ws must be 16-byte aligned");
+
+  ChainParams p;
+  p.n_layers = n_layers; p.n = n; p.h = h; p.w = w;
+  p.tiles_x = tg_ceil_div(w, TW);
+  p.tiles_y = tg_ceil_div(h, TH);
+  p.num_tiles = p.tiles_x * p.tiles_y * n;
+  p.sync = reinterpret_cast<uint32_t*>(sync_ws);
+  p.idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.dbg = tg_conv_timer_buffer();
+
+  EncodeTiledFn fn = chain_encode_fn();
+  TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  const void* bufs[kMaxMaps];
+  int n_maps = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const tg_chain_layer& s = layers[l];
+    TG_REQUIRE(s.x && s.weights && s.bias && s.y, TG_E_INVALID, "conv_chain: layer %d: null pointer", l);
+    TG_REQUIRE(s.act >= TG_ACT_NONE && s.act <= TG_ACT_LRELU02, TG_E_INVALID, "conv_chain: layer %d: act", l);
+    TG_REQUIRE(s.reserved == 0, TG_E_INVALID, "conv_chain: layer %d: reserved must be 0", l);
+    TG_REQUIRE(s.y != s.x, TG_E_INVALID, "conv_chain: layer %d: y aliases x (halo reads of other tiles)", l);
+    TG_REQUIRE(((uintptr_t)s.x & 15) == 0 && ((uintptr_t)s.y & 31) == 0 && ((uintptr_t)s.weights & 15) == 0 &&
+                   ((uintptr_t)s.residual & 31) == 0 && ((uintptr_t)s.bias & 3) == 0,
+               TG_E_INVALID, "conv_chain: layer %d: pointer alignment", l);
+    int m = -1;
+    for (int i = 0; i < n_maps; ++i)
+      if (bufs[i] == s.x) m = i;
+    if (m < 0) {
+      TG_REQUIRE(n_maps < kMaxMaps, TG_E_UNSUPPORTED, "conv_chain: more than %d distinct input buffers", kMaxMaps);
+      cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+      cuuint64_t strides[3] = {128, (cuuint64_t)w * 128, (cuuint64_t)h * w * 128};
+      cuuint32_t box[4] = {64, (cuuint32_t)BOXW, (cuuint32_t)BOXH, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = fn(&p.maps[n_maps], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(s.x), dims, strides,
+                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      TG_REQUIRE(r == CUDA_SUCCESS, TG_E_DRIVER, "conv_chain: cuTensorMapEncodeTiled failed (%d)", (int)r);
+      bufs[n_maps] = s.x;
+      m = n_maps++;
+    }
+    p.layers[l].w = reinterpret_cast<const unsigned char*>(s.weights);
+    p.layers[l].bias = s.bias;
+    p.layers[l].res = reinterpret_cast<const __half*>(s.residual);
+    p.layers[l].y = reinterpret_cast<__half*>(s.y);
+    p.layers[l].map = m;
+    p.layers[l].act = s.act;
+  }
+  for (int i = n_maps; i < kMaxMaps; ++i) p.maps[i] = p.maps[0];
+  for (int l = n_layers; l < TG_CHAIN_MAX_LAYERS; ++l) p.layers[l] = p.layers[0];
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e = cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBytes);
+    if (e != cudaSuccess) attr_err = e;
+    e = cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) attr_err = e;
+  });
+  TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_chain: cudaFuncSetAttribute: %s",
+             cudaGetErrorString(attr_err));
+
+  int sms = 0;
+  int rc = tg_device_sm_count(&sms);
+  if (rc != TG_OK) return rc;
+  // every CTA must be resident at once (tiles wait on tiles of other CTAs): one CTA per SM at most
+  int grid = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t lerr = p.dbg ? tg_launch(conv_chain_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p)
+                           : tg_launch(conv_chain_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p);
+  TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "conv_chain: launch failed: %s", cudaGetErrorString(lerr));
+  TG_CUDA_LAUNCH_CHECK("conv_chain");
+  return TG_OK;
+}
+
+}  // extern "C"

@@ -163,9 +163,10 @@ __device__ __forceinline__ float tg_upsample_at(const float* __restrict__ src, i
   }
 }
 
-__device__ __forceinline__ float tg_act(float v, int act) {
-  if (act == TG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == TG_ACT_LRELU02) return v >= 0.f ? v : 0.2f * v;
-  return v;
+// branch-free: act(v) = max(v, slope*v) with slope 1 (none) / 0 (ReLU) / 0.2 (LeakyReLU); `act` is
+// warp-uniform, so the slope selection hoists out of the per-element epilogue loops
+__device__ __forceinline__ float tg_act_slope(int act) {
+  return act == TG_ACT_NONE ? 1.f : (act == TG_ACT_RELU ? 0.f : 0.2f);
 }
+__device__ __forceinline__ float tg_act(float v, int act) { return fmaxf(v, v * tg_act_slope(act)); }
 #endif  // __CUDACC__

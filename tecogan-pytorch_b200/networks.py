@@ -136,6 +136,7 @@ class SRNet(nn.Module):
         self.conv_out = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
         self.upsample_func = upsample_func
         self._cache = _ConvCache()
+        self._chain = None
 
     def forward(self, lr_curr, hr_prev_tran):
         """lr_curr nchw, hr_prev_tran n(s*s*c)hw (both fp32) -> hr nchw fp32"""
@@ -146,10 +147,25 @@ class SRNet(nn.Module):
     def run_nhwc(self, x, lr_curr, out=None):
         """x = SRNet input NHWC fp16 [n,h,w,64] (channels [lr_curr | space_to_depth(warp) | 0])."""
         c = self._cache
-        a = c.get('in', self.conv_in[0], L.CONV_3X3, _RELU)(x)
+        body = [c.get('in', self.conv_in[0], L.CONV_3X3, _RELU)]
         for i, blk in enumerate(self.resblocks):
-            t = c.get(('r', i, 0), blk.conv[0], L.CONV_3X3, _RELU)(a)
-            a = c.get(('r', i, 2), blk.conv[2], L.CONV_3X3, L.ACT_NONE)(t, residual=a)
+            body += [c.get(('r', i, 0), blk.conv[0], L.CONV_3X3, _RELU),
+                     c.get(('r', i, 2), blk.conv[2], L.CONV_3X3, L.ACT_NONE)]
+        if (ops.chain_enabled() and ops.default_conv_impl() == 'tcgen05' and x.shape[-1] == 64
+                and ops.ConvChain.supported(body)):
+            # conv_in + all residual blocks in ONE persistent launch: buffers 0 = x (read only),
+            # 1 = block input/output (conv2 writes it in place over its own residual), 2 = conv1 output
+            if self._chain is None or [s[0] for s in self._chain.specs] != body:
+                specs = [(body[0], 0, 1, None)]
+                for i in range(len(self.resblocks)):
+                    specs += [(body[1 + 2 * i], 1, 2, None), (body[2 + 2 * i], 2, 1, 1)]
+                self._chain = ops.ConvChain(specs)
+            a = self._chain([x, torch.empty_like(x), torch.empty_like(x)])
+        else:
+            a = body[0](x)
+            for i in range(len(self.resblocks)):
+                t = body[1 + 2 * i](a)
+                a = body[2 + 2 * i](t, residual=a)
         for u in range(0, len(self.conv_up), 2):
             a = c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU)(a)
         # out = conv_out(a) (pure-store epilogue), then out += upsample_func(lr_curr)

@@ -212,6 +212,66 @@ def check_conv_vs_simt(a_mode=None, cin=64, cout=64, h=134, w=320, n=1, kind=Non
     return {'rel_max': e, 'frac_diff': frac}
 
 
+def check_conv_chain(n=2, h=37, w=29, blocks=2, max_ctas=0, repeats=1, seed=50):
+    """tg_conv_chain_tcgen05 (conv_in + `blocks` residual blocks in ONE persistent launch, tiles
+    gated by progress flags) vs the same layers as 1+2*blocks launches of tg_conv_tcgen05 on
+    identical packed weights.  Only the fp32 summation order differs (two partial accumulators),
+    so after each layer's fp16 rounding the two agree to ~1 ulp; `repeats` relaunches on the same
+    workspace exercise the epoch stamping of the flags."""
+    bound = 1.2 / np.sqrt(9 * 64)
+    pcs = []
+    for i in range(1 + 2 * blocks):
+        act = L.ACT_RELU if (i == 0 or i % 2 == 1) else L.ACT_NONE
+        pcs.append(ops.PackedConv(rand(seed + 3 * i, 64, 64, 3, 3, lo=-bound, hi=bound).to(DEV),
+                                  rand(seed + 3 * i + 1, 64, lo=-0.2, hi=0.2).to(DEV), L.CONV_3X3, act))
+    specs = [(pcs[0], 0, 1, None)]
+    for b in range(blocks):
+        specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
+    chain = ops.ConvChain(specs)
+    worst, frac = 0.0, 0.0
+    for rep in range(repeats):
+        x = nhwc(rand(seed + 100 + rep, n, 64, h, w, lo=-1, hi=1), 64)
+        a = pcs[0](x)
+        for b in range(blocks):
+            t = pcs[1 + 2 * b](a)
+            a = pcs[2 + 2 * b](t, residual=a)
+        # poison the chain's work buffers: stale data must never be read before it is produced
+        b1 = torch.full_like(x, float('nan'))
+        b2 = torch.full_like(x, float('nan'))
+        y = chain([x, b1, b2], max_ctas=max_ctas)
+        torch.cuda.synchronize()
+        assert torch.isfinite(y.float()).all(), f'chain output has non-finite values (rep {rep})'
+        d = (y.float() - a.float()).abs()
+        e = float(d.max() / a.float().abs().max())
+        worst = max(worst, e)
+        frac = max(frac, float((d > 0).float().mean()))
+        assert e <= 4e-3, f'conv chain vs per-layer launches: rel max {e} (rep {rep}, n={n} h={h} w={w} blocks={blocks})'
+    return {'rel_max': worst, 'frac_diff': frac}
+
+
+def check_conv_chain_vs_reference(n=1, h=20, w=24, blocks=1, seed=70):
+    """conv chain vs the CPU fp32 reference of the same three layers (fp16-rounded between layers)."""
+    bound = 1.2 / np.sqrt(9 * 64)
+    ws = [rand(seed + 3 * i, 64, 64, 3, 3, lo=-bound, hi=bound) for i in range(1 + 2 * blocks)]
+    bs = [rand(seed + 3 * i + 1, 64, lo=-0.2, hi=0.2) for i in range(1 + 2 * blocks)]
+    acts = [L.ACT_RELU if (i == 0 or i % 2 == 1) else L.ACT_NONE for i in range(1 + 2 * blocks)]
+    pcs = [ops.PackedConv(ws[i].to(DEV), bs[i].to(DEV), L.CONV_3X3, acts[i]) for i in range(len(ws))]
+    specs = [(pcs[0], 0, 1, None)]
+    for b in range(blocks):
+        specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
+    x = rand(seed + 50, n, 64, h, w, lo=-1, hi=1)
+    xd = nhwc(x, 64)
+    y = ops.ConvChain(specs)([xd, torch.empty_like(xd), torch.empty_like(xd)])
+    torch.cuda.synchronize()
+    a = f16(_conv_ref(x, ws[0], bs[0], L.CONV_3X3, acts[0]))
+    for b in range(blocks):
+        t = f16(_conv_ref(a, ws[1 + 2 * b], bs[1 + 2 * b], L.CONV_3X3, acts[1 + 2 * b]))
+        a = f16(_conv_ref(t, ws[2 + 2 * b], bs[2 + 2 * b], L.CONV_3X3, acts[2 + 2 * b], a))
+    e = relmax(from_nhwc(y, 64).numpy(), a.numpy())
+    assert e <= 4e-3, f'conv chain vs CPU reference: rel max {e}'
+    return {'rel_max': e}
+
+
 def check_conv_epilogues(impl='tcgen05'):
     out = {}
     # flow head: 24*tanh(conv) -> NCHW fp32 [n,2,h,w]
@@ -486,6 +546,11 @@ CHECKS = {
     'conv_tc_vs_simt_halo_full': lambda: check_conv_vs_simt(L.AMODE_HALO),
     'conv_tc_vs_simt_halo_convT_full': lambda: check_conv_vs_simt(L.AMODE_HALO, kind=L.CONVT_3X3_S2),
     'conv_tc_vs_simt_halo_2cta': lambda: check_conv_vs_simt(L.AMODE_HALO, h=64, w=64, n=2, max_ctas=3),
+    'conv_chain_vs_reference': check_conv_chain_vs_reference,
+    'conv_chain_1tile': lambda: check_conv_chain(n=1, h=16, w=8, blocks=1),
+    'conv_chain_ragged_repeat': lambda: check_conv_chain(n=2, h=37, w=29, blocks=2, repeats=3),
+    'conv_chain_few_ctas': lambda: check_conv_chain(n=3, h=50, w=44, blocks=3, max_ctas=5, repeats=2),
+    'conv_chain_full': lambda: check_conv_chain(n=4, h=134, w=320, blocks=10, repeats=2),
     'step_golden_g1': lambda: check_step_golden('g1'),
     'step_golden_g15': lambda: check_step_golden('g15'),
     'step_golden_g2_stress': lambda: check_step_golden('g2'),

@@ -54,7 +54,50 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
     return out
 
 
+CHAIN_NAMES = ['prod_wait_flags', 'prod_wait_empty', 'mma_total', 'mma_wait', 'epi_wait_tfull', 'epi_total',
+               'kernel', 'tiles']
+
+
+def run_chain(blocks=10, n=4, h=134, w=320):
+    """per-role timers of conv_chain_kernel (slots: tg_chain_tcgen05.cu CT_*)"""
+    dev = 'cuda:0'
+    nl = 1 + 2 * blocks
+    pcs = [ops.PackedConv(torch.randn(64, 64, 3, 3, device=dev) * 0.04, torch.zeros(64, device=dev), L.CONV_3X3,
+                          L.ACT_RELU if (i == 0 or i % 2 == 1) else L.ACT_NONE) for i in range(nl)]
+    specs = [(pcs[0], 0, 1, None)]
+    for b in range(blocks):
+        specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
+    chain = ops.ConvChain(specs)
+    x = torch.randn(n, h, w, 64, device=dev).half()
+    bufs = [x, torch.empty_like(x), torch.empty_like(x)]
+    for _ in range(3):
+        chain(bufs)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    lib = L.load()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    chain(bufs)
+    e1.record()
+    torch.cuda.synchronize()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
+    t = buf.view(148, 16).cpu().double()
+    t = t[t[:, 6] > 0]
+    tiles = t[:, 7].mean().item()
+    out = {'layer': f'chain {nl} layers n{n} {h}x{w}', 'us': e0.elapsed_time(e1) * 1e3, 'ctas': int(t.shape[0]),
+           'tile_layers_per_cta': tiles}
+    for i, nm in enumerate(CHAIN_NAMES[:-1]):
+        out[nm] = round(t[:, i].mean().item())
+    out['per_tile'] = {nm: round(out[nm] / max(tiles, 1)) for nm in CHAIN_NAMES[:7]}
+    print(json.dumps(out))
+    return out
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'chain':
+        run_chain()
+        run_chain(blocks=1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'pair':
         for flags in ('0', '16'):
             os.environ['TG_DBG_FLAGS'] = flags

@@ -2,22 +2,22 @@
 // warp-specialised tcgen05 launch for sm_100a -- the layer loop lives inside the kernel.
 //
 //   tiles   : 16x8 output pixels (M = 128), static assignment tile = cta + k*grid for every layer
-//   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 3 stages; the nine
+//   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 4 stages; the nine
 //             taps are nine shifted UMMA-descriptor views of the box (see tg_conv_tcgen05.cu)
-//   B       : the layer's 73.7 KB of packed weights resident in smem, DOUBLE buffered: layer l+1's
-//             weights stream in while layer l computes (the buffer is released by a tcgen05.commit
-//             behind the last MMA of layer l-1)
-//   D       : one 64-column fp32 accumulator per tile, 8 tiles in flight in TMEM.  (Measured: the
-//             tensor pipe spends ~39 cycles per 128x64x16 MMA plus the time the epilogue needs to
-//             read the accumulator back -- TMEM reads run at 64 B/cycle and do not overlap the
-//             MMAs -- so the accumulator is NOT split into partial sums: that doubles the reads.)
+//   B       : packed weights resident in smem in a ring of 14 tap slots (tap t of layer l in slot
+//             (9l + t) % 14): the next layer's taps 0-4 stream in while the current layer computes,
+//             taps 5-8 reuse the slots that the LAST tile of the current layer hands back (a
+//             tcgen05.commit behind its taps 0-3) -- no weight-reload bubble at layer boundaries and
+//             40 KB less shared memory than a double buffer (4 A stages instead of 3)
+//   D       : one 64-column fp32 accumulator per tile, 8 tiles in flight in TMEM (splitting the taps
+//             over two partial accumulators was measured: no gain).
 //   layers  : a tile of layer l needs the tiles of layer l-1 under its halo.  Epilogue groups
 //             publish `flags[tile] = epoch*32 + l + 1` (release, gpu scope) after their stores; a
-//             checker warp polls the <= 9 flags of up to three upcoming tiles per round (27 lanes)
+//             checker warp polls the <= 9 flags of each of the next nine tiles (sliding window)
 //             ahead of the TMA producer and hands it an in-order "verified" counter.  No launch,
 //             pipeline fill/drain, weight reload bubble or grid barrier between layers.
-//   roles   : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 dependency
-//             checker, warps 4..11 two epilogue groups alternating tiles.
+//   roles   : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + weight streamer,
+//             warp 3 dependency checker, warps 4..11 two epilogue groups alternating tiles.
 //
 // Replaces the 21 nn.Conv2d launches of SRNet.conv_in / ResidualBlock (tecogan_nets.py:92-100,
 // 111-116, 139-141) per step.
@@ -30,26 +30,22 @@
 #include "tg_epilogue.cuh"
 #include "tg_tcgen05.cuh"
 
-#ifndef TG_CHAIN_EXP
-#define TG_CHAIN_EXP 0   // non-zero values are timing experiments (wrong results); never shipped
-#endif
-
 namespace {
 
 constexpr int TH = 16, TW = 8, BOXW = TW + 2, BOXH = TH + 2;
 constexpr int kThreads = 384;
 constexpr int kMaxMaps = 4;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
+constexpr int kSlots = 14;                              // weight ring: tap t of layer l lives in slot (9l + t) % kSlots
 constexpr int kBufs = 8;                               // tiles in flight in TMEM (8 x 64 columns)
 constexpr uint32_t kAccStride = 64;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTapWBytes = 64 * 128;              // one tap: [64 cout rows][64 cin] fp16
-constexpr uint32_t kWBytes = 9 * kTapWBytes;           // 73,728 per layer
 constexpr uint32_t kHaloBytes = BOXW * BOXH * 128;     // 23,040
 constexpr uint32_t kStageBytes = (kHaloBytes + 1023u) & ~1023u;
 constexpr uint32_t kOffBias = 1024;                    // [layers][64] fp32
 constexpr uint32_t kOffW = kOffBias + TG_CHAIN_MAX_LAYERS * 256;
-constexpr uint32_t kOffStage = kOffW + 2 * kWBytes;
+constexpr uint32_t kOffStage = kOffW + kSlots * kTapWBytes;
 constexpr uint32_t kSmemBytes = 1024 /*align slack*/ + kOffStage + kStages * kStageBytes;
 static_assert(kOffW % 1024 == 0 && kOffStage % 1024 == 0, "swizzle atoms need 1024B alignment");
 static_assert(kSmemBytes <= 232448, "227 KB opt-in shared memory limit");
@@ -81,8 +77,8 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t saddr) {
   uint32_t v;
@@ -91,6 +87,26 @@ __device__ __forceinline__ uint32_t ld_acquire_cta_shared(uint32_t saddr) {
 }
 __device__ __forceinline__ void st_release_cta_shared(uint32_t saddr, uint32_t v) {
   asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+// non-blocking phase test (mbarrier.try_wait may suspend the thread for a while)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// named barrier over `nthreads` threads + AND-reduction of a predicate
+__device__ __forceinline__ uint32_t named_bar_red_and(int id, int nthreads, uint32_t pred) {
+  uint32_t out;
+  asm volatile(
+      "{\n.reg .pred p, q;\nsetp.ne.b32 q, %3, 0;\nbar.red.and.pred p, %1, %2, q;\nselp.b32 %0, 1, 0, p;\n}\n"
+      : "=r"(out)
+      : "r"(id), "r"(nthreads), "r"(pred)
+      : "memory");
+  return out;
 }
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 // generic-proxy global writes <-> async-proxy (TMA) global reads
@@ -107,7 +123,11 @@ __device__ __forceinline__ void ld_global_256_l2(const void* ptr, uint4& a, uint
 }
 
 enum { CT_PROD_FLAGS = 0, CT_PROD_EMPTY, CT_MMA_TOTAL, CT_MMA_WAIT, CT_EPI_TFULL, CT_EPI_TOTAL, CT_KERNEL, CT_TILES,
+       CT_MMA_ISSUE0, CT_MMA_LOOK, CT_MMA_ISSUE1, CT_MMA_BOUNDARY,
        CT_SLOTS = 16 };
+
+// event trace of CTA 0 (TIMING builds): trace[seq * 8 + event] = clock64, behind the 148 x 16 timer slots
+#define CT_TRACE(seq, ev) do { if (timing && b == 0) cp.dbg[148 * CT_SLOTS + (size_t)(seq) * 8 + (ev)] = clock64(); } while (0)
 
 template <bool TIMING>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -120,15 +140,16 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   const long long t_kernel0 = timing ? clock64() : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = base;                 // [kStages]
-  const uint32_t bar_empty = base + 32;           // [kStages]
-  const uint32_t bar_tfull = base + 64;           // [kBufs]
-  const uint32_t bar_tempty = base + 128;         // [kBufs]
-  const uint32_t bar_wfull = base + 192;          // [2] weights of the layer landed
-  const uint32_t bar_wfree = base + 208;          // [2] every MMA that read the buffer retired
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 224);
-  volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 228);
-  const uint32_t deps_ok_addr = base + 232;       // tiles (in this CTA's sequence) whose dependencies are verified
+  const uint32_t bar_full = base;                 // [kStages <= 8]
+  const uint32_t bar_empty = base + 64;           // [kStages <= 8]
+  const uint32_t bar_tfull = base + 128;          // [kBufs]
+  const uint32_t bar_tempty = base + 192;         // [kBufs]
+  const uint32_t bar_wfull = base + 256;          // [9] tap t of the current layer's weights landed
+  const uint32_t bar_wfree = base + 336;          // [9] every MMA of the layer that reads tap t retired
+  const uint32_t bar_wstart = base + 416;         // [1] the MMA issuer has taken delivery of a layer's weights
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 424);
+  volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 428);
+  const uint32_t deps_ok_addr = base + 432;       // tiles (in this CTA's sequence) whose dependencies are verified
   float* bias_s = reinterpret_cast<float*>(sm + kOffBias);
   const uint32_t smem_w0 = base + kOffW;
   const uint32_t smem_stage0 = base + kOffStage;
@@ -146,8 +167,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int i = 0; i < kBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 1); }
-    mbar_init(base + 240, 1);            // scratch barrier of the timing experiments
+    for (int i = 0; i < 9; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 1); }
+    mbar_init(bar_wstart, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
@@ -157,13 +178,11 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // Weights are static across the step (packed at module init / refresh, never by the predecessor
-  // kernel): the first two layers' weights are requested before joining the PDL wait.
-  if (warp == 0 && lane == 0) {
-    for (int l = 0; l < 2 && l < L; ++l) {
-      mbar_expect_tx(bar_wfull + 8 * l, kWBytes);
-      for (int t = 0; t < 9; ++t)
-        bulk_load(smem_w0 + l * kWBytes + t * kTapWBytes, cp.layers[l].w + (size_t)t * kTapWBytes, kTapWBytes,
-                  bar_wfull + 8 * l);
+  // kernel): layer 0's are requested, tap by tap, before joining the PDL wait.
+  if (warp == 2 && lane == 0) {
+    for (int t = 0; t < 9; ++t) {
+      mbar_expect_tx(bar_wfull + 8 * t, kTapWBytes);
+      bulk_load(smem_w0 + t * kTapWBytes, cp.layers[0].w + (size_t)t * kTapWBytes, kTapWBytes, bar_wfull + 8 * t);
     }
   }
   tg_pdl_wait();
@@ -171,7 +190,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   for (int i = threadIdx.x; i < L * 64; i += kThreads) bias_s[i] = cp.layers[i >> 6].bias[i & 63];
   if (threadIdx.x == 0) {
     *epoch_s = ld_acquire_gpu(cp.sync);
-    *reinterpret_cast<volatile uint32_t*>(sm + 232) = (uint32_t)n_my;   // layer 0 has no dependencies
+    *reinterpret_cast<volatile uint32_t*>(sm + 432) = (uint32_t)n_my;   // layer 0 has no dependencies
   }
   __syncthreads();
   const uint32_t fbase = (*epoch_s) << 5;              // flags of this launch: fbase + layers done
@@ -180,7 +199,6 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     // ============================================================ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    const int kpre = n_my - 1 < 4 ? n_my - 1 : 4;       // tile index at which layer l+1's weights are requested
     long long tw_flags = 0, tw_empty = 0;
     for (int l = 0; l < L; ++l) {
       const CUtensorMap* map = &cp.maps[cp.layers[l].map];
@@ -196,7 +214,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
           if (lane == 0 && ld_acquire_cta_shared(deps_ok_addr) <= seq) {
             const long long s0 = clock64();
             while (ld_acquire_cta_shared(deps_ok_addr) <= seq) {
-              __nanosleep(32);                          // do not hammer shared memory: the MMA operands need it
+              __nanosleep(20);                          // do not hammer shared memory: the MMA operands need it
               if (clock64() - s0 > 3000000000LL) {
                 if (b < 2) printf("tg_conv_chain: dependency timeout block=%d layer=%d tile=%d\n", b, l, tile);
                 __trap();
@@ -208,19 +226,12 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         }
         if (lane == 0) {
           if (l > 0) fence_proxy_async_global();
-          if (k == kpre && l >= 1 && l + 1 < L) {
-            // layer l+1's weights replace layer l-1's: wait until its last MMA has retired
-            mbar_wait(bar_wfree + 8 * ((l + 1) & 1), (uint32_t)((l - 1) >> 1) & 1u, 8);
-            mbar_expect_tx(bar_wfull + 8 * ((l + 1) & 1), kWBytes);
-            for (int t = 0; t < 9; ++t)
-              bulk_load(smem_w0 + ((l + 1) & 1) * kWBytes + t * kTapWBytes,
-                        cp.layers[l + 1].w + (size_t)t * kTapWBytes, kTapWBytes, bar_wfull + 8 * ((l + 1) & 1));
-          }
           const long long t0 = timing ? clock64() : 0;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
           if (timing) tw_empty += clock64() - t0;
           mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
           tma_load_4d(smem_stage0 + stage * kStageBytes, map, bar_full + 8 * stage, 0, tx * TW - 1, ty * TH - 1, n);
+          CT_TRACE(l * n_my + k, 5);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -237,65 +248,79 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     const uint64_t a_hi = make_sdesc(0, (uint32_t)BOXW * 128u);   // 8-row groups = consecutive tile rows
     const uint64_t b_hi = make_sdesc(0, 1024u);
     const long long t_mma0 = timing ? clock64() : 0;
-    long long tw = 0;
-    mbar_wait(bar_wfull, 0, 3);
+    long long tw = 0, t_i0 = 0, t_lk = 0, t_i1 = 0, t_bd = 0;
     mbar_wait(bar_tempty, 1, 4);                 // fresh barrier: passes immediately
     mbar_wait(bar_full, 0, 5);
     tc_fence_after();
+    const uint32_t wb16 = (smem_w0 & 0x3FFFFu) >> 4;
     for (int g = 0; g < total; ++g) {
+      const bool first_k = k == 0;
       const bool last_k = k == n_my - 1;
+      const bool hand_over = last_k && l + 1 < L;      // weight slots go back to the streamer tap by tap
       const bool has_next = g + 1 < total;
       const int nstage = (stage + 1 == kStages) ? 0 : stage + 1;
       const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
       const int nbuf = (buf + 1 == kBufs) ? 0 : buf + 1;
       const uint32_t nbphase = (buf + 1 == kBufs) ? (bphase ^ 1u) : bphase;
       const uint32_t sa16 = ((smem_stage0 + stage * kStageBytes) & 0x3FFFFu) >> 4;
-      const uint32_t wb16 = ((smem_w0 + (uint32_t)(l & 1) * kWBytes) & 0x3FFFFu) >> 4;
       const uint32_t d0 = tmem_base + (uint32_t)buf * kAccStride;
+      const int slot0 = (9 * l) % kSlots;              // ring slot of this layer's tap 0
       bool next_ready = false;
+      if (lane == 0) CT_TRACE(g, 6);
+      if (first_k) {
+        // first tile of a layer: its weights were streamed in behind the previous layer (normally
+        // all nine taps have landed long ago)
+        const long long tb0 = timing ? clock64() : 0;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) mbar_wait(bar_wfull + 8 * tap, (uint32_t)l & 1u, 3);
+        tc_fence_after();
+        // only now may the streamer complete the NEXT phase of the wfull barriers (a parity wait is
+        // sound only while the waiter is at most one phase behind)
+        if (lane == 0) mbar_arrive(bar_wstart);
+        __syncwarp();
+        if (timing) t_bd += clock64() - tb0;
+      }
+      // The 36 MMAs are issued in two parts (taps 0-3 | taps 4-8).  On the last tile of a layer a
+      // commit behind each part hands those taps' ring slots back to the weight streamer.
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
+        const long long tp0 = timing ? clock64() : 0;
         if (elect_one_sync()) {
 #pragma unroll
-          for (int i = (part == 0 ? 0 : 28); i < (part == 0 ? 28 : 36); ++i) {
+          for (int i = (part == 0 ? 0 : 16); i < (part == 0 ? 16 : 36); ++i) {
             const int tap = i >> 2, kk = i & 3;
             const uint32_t off = (uint32_t)((tap / 3) * BOXW + tap % 3) * 8u;   // (dy+1, dx+1) pixels, 128 B each
-#if TG_CHAIN_EXP == 6      /* timing experiment: only 18 of the 36 MMAs */
-            if (i >= 18) continue;
-#endif
+            int slot = slot0 + tap;
+            if (slot >= kSlots) slot -= kSlots;
             umma_f16(d0, a_hi | (uint64_t)(sa16 + off + 2u * kk),
-                     b_hi | (uint64_t)(wb16 + (uint32_t)tap * (kTapWBytes >> 4) + 2u * kk), cp.idesc, i >= 1 ? 1u : 0u);
-#if TG_CHAIN_EXP == 5      /* timing experiment: every MMA twice into the SAME accumulator */
-            umma_f16(d0, a_hi | (uint64_t)(sa16 + off + 2u * kk),
-                     b_hi | (uint64_t)(wb16 + (uint32_t)tap * (kTapWBytes >> 4) + 2u * kk), cp.idesc, 1u);
-#endif
-#if TG_CHAIN_EXP == 2      /* timing experiment: a (dummy) commit after every tap */
-            if (kk == 3) umma_commit(base + 240);
-#endif
+                     b_hi | (uint64_t)(wb16 + (uint32_t)slot * (kTapWBytes >> 4) + 2u * kk), cp.idesc, i >= 1 ? 1u : 0u);
+          }
+          if (hand_over) {
+#pragma unroll
+            for (int tap = (part == 0 ? 0 : 4); tap < (part == 0 ? 4 : 9); ++tap) umma_commit(bar_wfree + 8 * tap);
           }
           if (part == 1) {
             umma_commit(bar_empty + 8 * stage);
             umma_commit(bar_tfull + 8 * buf);
-            if (last_k) umma_commit(bar_wfree + 8 * (l & 1));
           }
         }
         __syncwarp();
+        if (timing) { if (part == 0) t_i0 += clock64() - tp0; else t_i1 += clock64() - tp0; }
+        const long long tl0 = timing ? clock64() : 0;
         if (part == 0 && has_next) {
-          // look ahead while 28 MMAs are queued in the tensor pipe -- but never BLOCK before this
-          // tile is committed: the next tile may (transitively) depend on this one through the flags
-          uint32_t r = mbar_try_wait(bar_tempty + 8 * nbuf, nbphase ^ 1);
-          if (last_k) r &= mbar_try_wait(bar_wfull + 8 * ((l + 1) & 1), (uint32_t)((l + 1) >> 1) & 1u);
-          r &= mbar_try_wait(bar_full + 8 * nstage, nphase);
+          // look ahead while MMAs are queued in the tensor pipe -- but never BLOCK before this tile
+          // is committed: the next tile may (transitively) depend on this one through the flags
+          // (test_wait: try_wait may suspend the warp for hundreds of cycles)
+          uint32_t r = mbar_test_wait(bar_tempty + 8 * nbuf, nbphase ^ 1);
+          r &= mbar_test_wait(bar_full + 8 * nstage, nphase);
           next_ready = __all_sync(0xFFFFFFFFu, r != 0);
-#if TG_CHAIN_EXP != 3     /* 3 = timing experiment: no tcgen05.fence::after_thread_sync in the loop */
           if (next_ready) tc_fence_after();
-#endif
+          if (timing) t_lk += clock64() - tl0;
         }
       }
       if (has_next && !next_ready) {
         const long long t0 = timing ? clock64() : 0;
         mbar_wait(bar_tempty + 8 * nbuf, nbphase ^ 1, 4);
-        if (last_k) mbar_wait(bar_wfull + 8 * ((l + 1) & 1), (uint32_t)((l + 1) >> 1) & 1u, 3);
         mbar_wait(bar_full + 8 * nstage, nphase, 5);
         if (timing) tw += clock64() - t0;
         tc_fence_after();
@@ -307,6 +332,32 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       cp.dbg[b * CT_SLOTS + CT_MMA_TOTAL] = clock64() - t_mma0;
       cp.dbg[b * CT_SLOTS + CT_MMA_WAIT] = tw;
       cp.dbg[b * CT_SLOTS + CT_TILES] = total;
+      cp.dbg[b * CT_SLOTS + CT_MMA_ISSUE0] = t_i0;
+      cp.dbg[b * CT_SLOTS + CT_MMA_LOOK] = t_lk;
+      cp.dbg[b * CT_SLOTS + CT_MMA_ISSUE1] = t_i1;
+      cp.dbg[b * CT_SLOTS + CT_MMA_BOUNDARY] = t_bd;
+    }
+  } else if (warp == 2) {
+    // ============================================================ weight streamer
+    // Weights live in a ring of kSlots tap slots (tap t of layer l in slot (9l + t) % kSlots).  The
+    // next layer's first kSlots - 9 taps stream in while the current layer computes; its remaining
+    // taps reuse the slots the LAST tile of the current layer hands back after its first taps, so
+    // they land before the next layer's first tile gets to them: no reload bubble, and 40 KB less
+    // shared memory than a double buffer (one more A stage).
+    if (lane == 0) {
+      for (int l = 1; l < L; ++l) {
+        mbar_wait(bar_wstart, (uint32_t)(l - 1) & 1u, 9);   // layer l-1's weights have been taken over
+        for (int t = 0; t < 9; ++t) {
+          const int gi = 9 * l + t;                     // global tap index; its slot's previous tenant is gi - kSlots
+          if (gi >= kSlots) {
+            const int pl = (gi - kSlots) / 9, pt = (gi - kSlots) - pl * 9;
+            mbar_wait(bar_wfree + 8 * pt, (uint32_t)pl & 1u, 8);
+          }
+          mbar_expect_tx(bar_wfull + 8 * t, kTapWBytes);
+          bulk_load(smem_w0 + (uint32_t)(gi % kSlots) * kTapWBytes, cp.layers[l].w + (size_t)t * kTapWBytes,
+                    kTapWBytes, bar_wfull + 8 * t);
+        }
+      }
     }
   } else if (warp == 3) {
     // ============================================================ dependency checker
@@ -317,7 +368,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     // through a shared-memory counter and the window slides on.
     constexpr int R = 3, W = 3 * R;
     const int sub = lane / 9, nbr = lane - sub * 9;
-    int q[R];
+    int q[R] = {0, 0, 0};
     const uint32_t* f[R];
     uint32_t need[R];
     bool ok[R];
@@ -362,7 +413,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       if (p > 0) {
         fence_acq_rel_gpu();                            // relaxed polls + fence = acquire (every lane)
         __syncwarp();                                   // the other lanes' acquires happen-before the publication
-        if (lane == 0) st_release_cta_shared(deps_ok_addr, (uint32_t)(head + p));
+        if (lane == 0) {
+          st_release_cta_shared(deps_ok_addr, (uint32_t)(head + p));
+          for (int i = 0; i < p; ++i) CT_TRACE(head + i, 4);
+        }
         head += p;
 #pragma unroll
         for (int rr = 0; rr < R; ++rr)
@@ -383,6 +437,20 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     const uint32_t lane_bits = (uint32_t)(q * 32) << 16;
     long long te_tfull = 0;
     const long long t_epi0 = timing ? clock64() : 0;
+    // Publication of a finished tile (flag = layers done, release at gpu scope) is DEFERRED: the
+    // gpu-scope fence has to wait until the tile's stores have reached L2, and done right after the
+    // stores it stalls the group for that round trip on every tile (measured: the epilogue became the
+    // bottleneck).  The group barrier at the top of the next tile orders the 128 threads' stores
+    // before thread 0 (CTA scope; its fence + release store is cumulative over them -- the
+    // grid-barrier pattern); thread 0 then publishes right before the NEXT tile's stores, when the
+    // old ones have long landed.  If the next accumulator is not ready yet the group would only
+    // wait, so it publishes at once -- a tile is never held back while its CTA is idle, which also
+    // keeps the dependency graph free of cycles.  The consumers order the async proxy (TMA)
+    // behind their acquire with fence.proxy.async.
+    bool pending = false;
+    uint32_t* pend_flag = nullptr;
+    uint32_t pend_val = 0;
+    int pend_seq = 0;
     for (int g = grp; g < total; g += 2) {
       const int l = g / n_my, k = g - l * n_my;
       const int buf = g & (kBufs - 1);
@@ -404,21 +472,24 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         for (int i = 0; i < 8; i += 2) ld_global_256_l2(rp + i, res[i], res[i + 1]);
       }
       const long long t0 = timing ? clock64() : 0;
-      mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+      const uint32_t acc_ready = named_bar_red_and(1 + grp, 128, mbar_test_wait(bar_tfull + 8 * buf, bphase));
+      if (!acc_ready) {
+        if (pending) {
+          if (gtid == 0) { fence_acq_rel_gpu(); st_relaxed_gpu(pend_flag, pend_val); CT_TRACE(pend_seq, 3); }
+          pending = false;
+        }
+        mbar_wait(bar_tfull + 8 * buf, bphase, 7);
+      }
       if (timing) te_tfull += clock64() - t0;
+      if (gtid == 0) CT_TRACE(g, 1);
       tc_fence_after();
       uint4* orow = reinterpret_cast<uint4*>(ly.y + pix * 64);
       const uint32_t tad = tmem_base + (uint32_t)buf * kAccStride + lane_bits;
 #pragma unroll
       for (int pc = 0; pc < 2; ++pc) {
         uint32_t v[32];
-#if TG_CHAIN_EXP == 1   /* timing experiment: no TMEM read-back (wrong results) */
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0;
-#else
         tmem_ld32(tad + pc * 32, v);
         tmem_ld_wait();
-#endif
         if (pc == 1) {
           tc_fence_before();
           __syncwarp();
@@ -446,24 +517,26 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
             o[j] = __floats2half2_rn(a0, a1);
           }
         }
+        if (pc == 0 && pending) {
+          if (gtid == 0) { fence_acq_rel_gpu(); st_relaxed_gpu(pend_flag, pend_val); CT_TRACE(pend_seq, 3); }
+          pending = false;
+        }
         if (inb) {
           st_global_256(orow + pc * 4, ov[0], ov[1]);
           st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
         }
       }
+      if (gtid == 0) CT_TRACE(g, 2);
       if (l + 1 < L) {
-        // Publish the tile.  bar.sync orders the 128 threads' stores before thread 0 (CTA scope);
-        // its gpu-scope fence + release store is cumulative over them (the grid-barrier pattern:
-        // __syncthreads(); if (tid == 0) { __threadfence(); flag = 1; }).  One fence per tile, not
-        // one per thread: the fence has to wait for the stores to reach L2 and the group cannot
-        // take its next tile before it returns -- 128 of them made the epilogue the bottleneck.
-        // The consumers order the async proxy (TMA) behind their acquire with fence.proxy.async.
-        named_bar_sync(1 + grp, 128);
-        if (gtid == 0) {
-          fence_acq_rel_gpu();
-          st_release_gpu(flags + tile, fbase + (uint32_t)l + 1u);
-        }
+        pending = true;
+        pend_flag = flags + tile;
+        pend_val = fbase + (uint32_t)l + 1u;
+        pend_seq = g;
       }
+    }
+    if (pending) {
+      named_bar_sync(1 + grp, 128);
+      if (gtid == 0) { fence_acq_rel_gpu(); st_relaxed_gpu(pend_flag, pend_val); CT_TRACE(pend_seq, 3); }
     }
     if (timing && gtid == 0 && grp == 0) {
       cp.dbg[b * CT_SLOTS + CT_EPI_TFULL] = te_tfull;

@@ -55,7 +55,7 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
 
 
 CHAIN_NAMES = ['prod_wait_flags', 'prod_wait_empty', 'mma_total', 'mma_wait', 'epi_wait_tfull', 'epi_total',
-               'kernel', 'tiles']
+               'kernel', 'tiles', 'mma_issue0', 'mma_look', 'mma_issue1', 'mma_boundary']
 
 
 def run_chain(blocks=10, n=4, h=134, w=320):
@@ -72,7 +72,7 @@ def run_chain(blocks=10, n=4, h=134, w=320):
     bufs = [x, torch.empty_like(x), torch.empty_like(x)]
     for _ in range(3):
         chain(bufs)
-    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 16 + 8 * 24 * 16, dtype=torch.int64, device=dev)
     lib = L.load()
     lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -81,22 +81,50 @@ def run_chain(blocks=10, n=4, h=134, w=320):
     e1.record()
     torch.cuda.synchronize()
     lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
+    trace = buf[148 * 16:].view(-1, 8).cpu()
+    buf = buf[:148 * 16]
     t = buf.view(148, 16).cpu().double()
     t = t[t[:, 6] > 0]
     tiles = t[:, 7].mean().item()
     out = {'layer': f'chain {nl} layers n{n} {h}x{w}', 'us': e0.elapsed_time(e1) * 1e3, 'ctas': int(t.shape[0]),
            'tile_layers_per_cta': tiles}
-    for i, nm in enumerate(CHAIN_NAMES[:-1]):
-        out[nm] = round(t[:, i].mean().item())
-    out['per_tile'] = {nm: round(out[nm] / max(tiles, 1)) for nm in CHAIN_NAMES[:7]}
+    for i, nm in enumerate(CHAIN_NAMES):
+        if nm != 'tiles':
+            out[nm] = round(t[:, i].mean().item())
+    out['per_tile'] = {nm: round(out[nm] / max(tiles, 1)) for nm in CHAIN_NAMES if nm != 'tiles'}
     print(json.dumps(out))
+    # distribution over CTAs: the CTAs that never wait for flags are the critical path
+    full = buf.view(148, 16).cpu().double()
+    order = torch.argsort(full[:, 0])
+    for tag, idx in (('least flag wait', order[:3].tolist()), ('most flag wait', order[-3:].tolist())):
+        for c in idx:
+            print(json.dumps({'cta': c, 'which': tag, **{nm: int(full[c, i].item()) for i, nm in enumerate(CHAIN_NAMES)}}))
+    # event trace of CTA 0: per tile [_, acc ready, stores issued, published, deps verified, TMA issued, MMA start, _]
+    nmy = int(full[0, 7].item()) // nl
+    tr = trace[:nmy * nl].double()
+    def stat(x):
+        x = x[torch.isfinite(x)]
+        return [int(v) for v in torch.quantile(x, torch.tensor([0.1, 0.5, 0.9], dtype=torch.double)).tolist()] if len(x) else None
+    sel = torch.arange(nmy, nmy * (nl - 1))
+    ev = {
+        'epilogue: acc ready -> stores issued (E2-E1)': tr[sel, 2] - tr[sel, 1],
+        'publish: stores issued -> flag released (E3-E2)': tr[sel, 3] - tr[sel, 2],
+        'own tile published -> next-layer same tile verified (E4[q]-E3[q-n])': tr[sel, 4] - tr[sel - nmy, 3],
+        'verified -> TMA issued (E5-E4)': tr[sel, 5] - tr[sel, 4],
+        'TMA issued -> MMA start (E6-E5)': tr[sel, 6] - tr[sel, 5],
+        'MMA start -> acc ready (E1-E6)': tr[sel, 1] - tr[sel, 6],
+        'MMA start(q+1) - MMA start(q)': tr[sel + 1, 6] - tr[sel, 6],
+        'lead: TMA issue(q) - MMA start(q-3)': tr[sel, 5] - tr[sel - 3, 6],
+    }
+    print(json.dumps({'trace_cta0 p10/p50/p90 cycles': {k: stat(v) for k, v in ev.items()}}))
+    q = torch.quantile(full[:, :12], torch.tensor([0.0, 0.5, 1.0], dtype=torch.double), dim=0)
+    print(json.dumps({'min/med/max': {nm: [int(q[j, i].item()) for j in range(3)] for i, nm in enumerate(CHAIN_NAMES)}}))
     return out
 
 
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'chain':
         run_chain()
-        run_chain(blocks=1)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'pair':
         for flags in ('0', '16'):

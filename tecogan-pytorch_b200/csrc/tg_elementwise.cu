@@ -39,13 +39,17 @@ __device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, 
 //   LRFLOW: the LR flow neighbourhood ((RY+3) rows x LRW+3 cols, reflect-padded + replicate-clamped)
 //   is staged in smem once; each thread evaluates the x-pass of the separable 4-tap upsampler for its
 //   own column into registers (RY+3 values per component) and the y-pass per HR row.
-template <int S, bool LRFLOW, int RY>
+//   FLOW: 0 = HR flow given; 1 / 2 = LR flow, upsampled inline with the bicubic / bilinear
+//   upsample_func (compile time, so the y-pass taps are immediates).
+template <int S, int FLOW, int RY>
 __global__ void __launch_bounds__(128)
 warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                        const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
-                       int w, int h8, int w8, int up_mode, int cpad) {
+                       int w, int h8, int w8, int cpad) {
   tg_pdl_wait();
   tg_pdl_trigger();
+  constexpr bool LRFLOW = FLOW != 0;
+  constexpr int up_mode = FLOW == 2 ? TG_UP_BILINEAR : TG_UP_BICUBIC;
   constexpr int LRW = 128 / S;
   constexpr int FW = LRW + 3;                 // LR columns x0-1 .. x0+LRW+1
   constexpr int FH = RY + 3;                  // LR rows    y0-1 .. y0+RY+1
@@ -60,7 +64,9 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
   const int H = h * S, W = w * S;
   const int X = x0 * S + t;             // HR column of this thread
   const int lx = t / S, sx = t - lx * S;
-  const int used = (S * S + 1) * C;
+
+  // the pad channels [(S*S+1)*C, cpad) are never written again: zero the whole tile once
+  for (int i = t; i < LRW * cpad / 8; i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
 
   float hx[2][FH];                      // x-pass of the flow upsampler, this thread's column
   if (LRFLOW) {
@@ -87,11 +93,8 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
   for (int ry = 0; ry < RY; ++ry) {
     const int y = y0 + ry;
     if (y >= h) break;                  // uniform over the CTA
-    // zero the pad channels [ (S*S+1)*C, cpad ) and stage lr_curr
-    for (int i = t; i < LRW * (cpad - used); i += 128) {
-      const int p = i / (cpad - used), k = i - p * (cpad - used);
-      tile[p * cpad + used + k] = __float2half(0.f);
-    }
+    if (ry == 0) __syncthreads();       // (tile zeroing / flow staging above) before the first channel writes
+    // stage lr_curr
     for (int i = t; i < LRW * C; i += 128) {
       const int k = i / LRW, p = i - k * LRW;
       const int xx = x0 + p;
@@ -121,7 +124,7 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
       if (C == 3) {
         // two-phase gather: compute the 4 corner offsets of all S pixels, issue all 12*S loads,
         // then combine -- 12*S independent loads in flight per thread hide the L2/DRAM latency
-        int o00[S], o01[S], o10[S], o11[S];
+        int o00[S];
         float ax[S], ay[S];
 #pragma unroll
         for (int sy = 0; sy < S; ++sy) {
@@ -129,11 +132,14 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
           float fy = (float)(y * S + sy) + v[sy];
           fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
           fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
-          const float x0f = floorf(fx), y0f = floorf(fy);
-          const int xa = (int)x0f, ya = (int)y0f;
-          const int xb = min(xa + 1, W - 1), yb = min(ya + 1, H - 1);
-          ax[sy] = fx - x0f; ay[sy] = fy - y0f;
-          o00[sy] = ya * W + xa; o01[sy] = ya * W + xb; o10[sy] = yb * W + xa; o11[sy] = yb * W + xb;
+          // The four corners are (ya,xa),(ya,xa+1),(ya+1,xa),(ya+1,xa+1) with xa <= W-2, ya <= H-2:
+          // at the far border (fx == W-1) the pair is shifted one to the left and the fraction
+          // becomes 1, which selects the same sample with weight exactly 1 (bit-identical result,
+          // net_utils.py:76 padding_mode='border') -- and the corner addresses are immediates of
+          // two base addresses instead of four independent ones.
+          const int xa = min((int)floorf(fx), W - 2), ya = min((int)floorf(fy), H - 2);
+          ax[sy] = fx - (float)xa; ay[sy] = fy - (float)ya;
+          o00[sy] = ya * W + xa;
         }
         float g[S][3][4];
         const float* img = hr_prev + (size_t)n * 3 * H * W;
@@ -141,9 +147,10 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
         for (int sy = 0; sy < S; ++sy)
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
-            const float* plane = img + (size_t)k * H * W;
-            g[sy][k][0] = __ldg(plane + o00[sy]); g[sy][k][1] = __ldg(plane + o01[sy]);
-            g[sy][k][2] = __ldg(plane + o10[sy]); g[sy][k][3] = __ldg(plane + o11[sy]);
+            const float* r0 = img + (size_t)k * H * W + o00[sy];
+            const float* r1 = r0 + W;
+            g[sy][k][0] = __ldg(r0); g[sy][k][1] = __ldg(r0 + 1);
+            g[sy][k][2] = __ldg(r1); g[sy][k][3] = __ldg(r1 + 1);
           }
 #pragma unroll
         for (int sy = 0; sy < S; ++sy) {
@@ -458,13 +465,17 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   dim3 grid(tg_ceil_div(w, lrw), tg_ceil_div(h, RY), n);
   const size_t smem = (size_t)lrw * cpad * sizeof(__half);
   __half* o = (__half*)out;
+  TG_REQUIRE(s * h >= 2 && s * w >= 2, TG_E_UNSUPPORTED, "warp_s2d_concat: HR image smaller than 2x2");
+  const int fm = !lrflow ? 0 : (up_mode == TG_UP_BICUBIC ? 1 : 2);
+#define TG_WARP_LAUNCH(SS, FM)                                                                              \
+  tg_launch(warp_s2d_concat_kernel<SS, FM, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, \
+            c, h, w, h8, w8, cpad)
   if (s == 4) {
-    if (lrflow) tg_launch(warp_s2d_concat_kernel<4, true, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        tg_launch(warp_s2d_concat_kernel<4, false, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (fm == 0) TG_WARP_LAUNCH(4, 0); else if (fm == 1) TG_WARP_LAUNCH(4, 1); else TG_WARP_LAUNCH(4, 2);
   } else {
-    if (lrflow) tg_launch(warp_s2d_concat_kernel<2, true, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
-    else        tg_launch(warp_s2d_concat_kernel<2, false, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, c, h, w, h8, w8, up_mode, cpad);
+    if (fm == 0) TG_WARP_LAUNCH(2, 0); else if (fm == 1) TG_WARP_LAUNCH(2, 1); else TG_WARP_LAUNCH(2, 2);
   }
+#undef TG_WARP_LAUNCH
   TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
   return TG_OK;
 }

@@ -115,9 +115,8 @@ int tg_conv_simt(const tg_conv_desc* d, void* stream);
  * layers over its fixed set of 16x8 tiles; a tile of layer l starts as soon as the (up to 9)
  * tiles of layer l-1 under its 18x10 halo have been published (per-tile progress flags in
  * `sync_ws`), so there is no launch, pipeline fill/drain or whole-grid barrier between layers,
- * and the next layer's weights are prefetched into a second shared-memory buffer.
- * Same arithmetic as n_layers calls of tg_conv_tcgen05 (fp32 accumulate; the nine taps are
- * summed in two interleaved partial accumulators).
+ * and the next layer's weights stream into a ring of shared-memory tap slots behind the current
+ * layer.  Bit-identical to n_layers calls of tg_conv_tcgen05.
  *   layers[l].x / y / residual : NHWC fp16 [n,h,w,64]; y[l] is normally x[l+1].  y[l] may alias
  *       residual[l] (in place) or a buffer last READ by layer <= l-1; it must not alias x[l].
  *       At most 4 distinct x buffers per chain.

@@ -608,8 +608,6 @@ int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int
   p.idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.dbg = tg_conv_timer_buffer();
 
-  EncodeTiledFn fn = chain_encode_fn();
-  TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
   const void* bufs[kMaxMaps];
   int n_maps = 0;
   for (int l = 0; l < n_layers; ++l) {
@@ -626,6 +624,8 @@ int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int
       if (bufs[i] == s.x) m = i;
     if (m < 0) {
       TG_REQUIRE(n_maps < kMaxMaps, TG_E_UNSUPPORTED, "conv_chain: more than %d distinct input buffers", kMaxMaps);
+      EncodeTiledFn fn = chain_encode_fn();
+      TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
       cuuint64_t dims[4] = {64, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
       cuuint64_t strides[3] = {128, (cuuint64_t)w * 128, (cuuint64_t)h * w * 128};
       cuuint32_t box[4] = {64, (cuuint32_t)BOXW, (cuuint32_t)BOXH, 1};

@@ -219,44 +219,91 @@ __global__ void maxpool2x2_kernel(const uint4* __restrict__ x, uint4* __restrict
 
 // F.interpolate(scale_factor=2, bilinear, align_corners=False):
 // out[2i] = .25*in[max(i-1,0)] + .75*in[i], out[2i+1] = .75*in[i] + .25*in[min(i+1,L-1)]
-__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h,
-                                  int w, int c8) {
+// One thread = one INPUT position (8 channels): 9 independent 16-byte loads of its 3x3 clamped
+// neighbourhood, four 16-byte outputs (the 2x2 block it expands to) -- 9 loads per 4 outputs
+// instead of 16, all in flight together, 32-bit index arithmetic.
+__device__ __forceinline__ void up2_mix(const uint4& a, const uint4& b, float wa, float wb, float2 o[4]) {
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = __half22float2(pa[k]), fb = __half22float2(pb[k]);
+    o[k].x = wa * fa.x + wb * fb.x;
+    o[k].y = wa * fa.y + wb * fb.y;
+  }
+}
+__device__ __forceinline__ uint4 up2_out(const float2 a[4], const float2 b[4], float wa, float wb) {
+  uint4 r;
+  __half2* rh = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 o;
+    o.x = wa * a[k].x + wb * b[k].x;
+    o.y = wa * a[k].y + wb * b[k].y;
+    rh[k] = __float22half2_rn(o);
+  }
+  return r;
+}
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int c8) {
   tg_pdl_wait();
   tg_pdl_trigger();
-  const int ho = 2 * h, wo = 2 * w;
-  const size_t total = (size_t)n * ho * wo * c8;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % c8);
-    size_t p = i / c8;
-    const int xo = (int)(p % wo); p /= wo;
-    const int yo = (int)(p % ho);
-    const int nn = (int)(p / ho);
-    const int yi = yo >> 1, xi = xo >> 1;
-    const int ya = (yo & 1) ? yi : max(yi - 1, 0), yb = (yo & 1) ? min(yi + 1, h - 1) : yi;
-    const int xa = (xo & 1) ? xi : max(xi - 1, 0), xb = (xo & 1) ? min(xi + 1, w - 1) : xi;
-    // weights on (a,b): odd -> (.75,.25), even -> (.25,.75)
-    const float wya = (yo & 1) ? 0.75f : 0.25f, wxa = (xo & 1) ? 0.75f : 0.25f;
-    const float wyb = 1.f - wya, wxb = 1.f - wxa;
-    const size_t rowa = ((size_t)nn * h + ya) * w, rowb = ((size_t)nn * h + yb) * w;
-    const uint4 vaa = __ldg(x + (rowa + xa) * c8 + cv), vab = __ldg(x + (rowa + xb) * c8 + cv);
-    const uint4 vba = __ldg(x + (rowb + xa) * c8 + cv), vbb = __ldg(x + (rowb + xb) * c8 + cv);
-    const __half2* paa = reinterpret_cast<const __half2*>(&vaa);
-    const __half2* pab = reinterpret_cast<const __half2*>(&vab);
-    const __half2* pba = reinterpret_cast<const __half2*>(&vba);
-    const __half2* pbb = reinterpret_cast<const __half2*>(&vbb);
-    uint4 r;
-    __half2* rh = reinterpret_cast<__half2*>(&r);
+  const int total = n * h * w * c8;
+  const int wo = 2 * w;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cv = i % c8;
+    int p = i / c8;
+    const int xi = p % w; p /= w;
+    const int yi = p % h;
+    const int nn = p / h;
+    const int ya = max(yi - 1, 0), yc = min(yi + 1, h - 1);
+    const int xa = max(xi - 1, 0), xc = min(xi + 1, w - 1);
+    const uint4* r0 = x + ((size_t)(nn * h + ya) * w) * c8 + cv;
+    const uint4* r1 = x + ((size_t)(nn * h + yi) * w) * c8 + cv;
+    const uint4* r2 = x + ((size_t)(nn * h + yc) * w) * c8 + cv;
+    const uint4 v00 = __ldg(r0 + xa * c8), v01 = __ldg(r0 + xi * c8), v02 = __ldg(r0 + xc * c8);
+    const uint4 v10 = __ldg(r1 + xa * c8), v11 = __ldg(r1 + xi * c8), v12 = __ldg(r1 + xc * c8);
+    const uint4 v20 = __ldg(r2 + xa * c8), v21 = __ldg(r2 + xi * c8), v22 = __ldg(r2 + xc * c8);
+    // x pass per row: even output column = .25*in[x-1] + .75*in[x], odd = .75*in[x] + .25*in[x+1]
+    float2 e0[4], o0[4], e1[4], o1[4], e2[4], o2[4];
+    up2_mix(v00, v01, 0.25f, 0.75f, e0); up2_mix(v01, v02, 0.75f, 0.25f, o0);
+    up2_mix(v10, v11, 0.25f, 0.75f, e1); up2_mix(v11, v12, 0.75f, 0.25f, o1);
+    up2_mix(v20, v21, 0.25f, 0.75f, e2); up2_mix(v21, v22, 0.75f, 0.25f, o2);
+    uint4* out0 = y + ((size_t)(nn * 2 * h + 2 * yi) * wo + 2 * xi) * c8 + cv;   // output row 2*yi
+    uint4* out1 = out0 + (size_t)wo * c8;                                       // output row 2*yi+1
+    out0[0] = up2_out(e0, e1, 0.25f, 0.75f);
+    out0[c8] = up2_out(o0, o1, 0.25f, 0.75f);
+    out1[0] = up2_out(e1, e2, 0.75f, 0.25f);
+    out1[c8] = up2_out(o1, o2, 0.75f, 0.25f);
+  }
+}
+
+// FNet input: cat([x1,x2],1) of two 3-channel NCHW fp32 images -> NHWC fp16 c64 (tecogan_nets.py:71).
+// One thread = one pixel: 2*c coalesced plane loads, then the pixel's whole 128-byte row (six
+// values + zeros) in four 256-bit stores -- full 32-byte sectors per store instruction.
+__global__ void __launch_bounds__(256)
+pack_pair_c64_kernel(const float* __restrict__ x1, const float* __restrict__ x2, uint4* __restrict__ y,
+                     int n, int c, int hw) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
+  const int total = n * hw;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int nn = i / hw, sp = i - nn * hw;
+    __align__(16) __half vals[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 aa = __half22float2(paa[k]), ab = __half22float2(pab[k]);
-      const float2 ba = __half22float2(pba[k]), bb = __half22float2(pbb[k]);
-      float2 o;
-      o.x = wya * (wxa * aa.x + wxb * ab.x) + wyb * (wxa * ba.x + wxb * bb.x);
-      o.y = wya * (wxa * aa.y + wxb * ab.y) + wyb * (wxa * ba.y + wxb * bb.y);
-      rh[k] = __float22half2_rn(o);
+    for (int k = 0; k < 8; ++k) {
+      float v = 0.f;
+      if (k < c) v = __ldg(x1 + ((size_t)nn * c + k) * hw + sp);
+      else if (k < 2 * c) v = __ldg(x2 + ((size_t)nn * c + (k - c)) * hw + sp);
+      vals[k] = __float2half(v);
     }
-    y[i] = r;
+    const uint4 v0 = *reinterpret_cast<const uint4*>(vals), z = make_uint4(0u, 0u, 0u, 0u);
+    uint4* row = y + (size_t)i * 8;
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(row), "r"(v0.x), "r"(v0.y),
+                 "r"(v0.z), "r"(v0.w), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+#pragma unroll
+    for (int q = 1; q < 4; ++q)
+      asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(row + 2 * q), "r"(z.x) : "memory");
   }
 }
 
@@ -507,7 +554,8 @@ int tg_upsample2x_bilinear_nhwc_f16(const void* x, void* y, int n, int h, int w,
                                     void* stream) {
   TG_REQUIRE(x && y, TG_E_INVALID, "upsample2x: null pointer");
   TG_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, TG_E_INVALID, "upsample2x: bad shape");
-  const size_t total = (size_t)n * (2 * h) * (2 * w) * (c / 8);
+  TG_REQUIRE((size_t)n * h * w * (c / 8) < (size_t)1 << 30, TG_E_UNSUPPORTED, "upsample2x: tensor too large");
+  const size_t total = (size_t)n * h * w * (c / 8);    // one thread per input position and 8-channel vector
   tg_launch(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const uint4*)x, (uint4*)y, n, h, w, c / 8);
   TG_CUDA_LAUNCH_CHECK("upsample2x");
   return TG_OK;
@@ -518,8 +566,12 @@ int tg_pack_pair_nhwc_f16(const float* x1, const float* x2, void* y, int n, int 
   TG_REQUIRE(x1 && x2 && y, TG_E_INVALID, "pack_pair: null pointer");
   TG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0 && cpad % 8 == 0 && 2 * c <= cpad, TG_E_INVALID,
              "pack_pair: bad shape");
-  const size_t total = (size_t)n * h * w * (cpad / 8);
-  tg_launch(pack_pair_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x1, x2, (uint4*)y, n, c, h, w, cpad / 8, 0, 1);
+  if (cpad == 64 && 2 * c <= 8 && (size_t)n * h * w < (size_t)1 << 30 && ((uintptr_t)y & 31) == 0) {
+    tg_launch(pack_pair_c64_kernel, dim3(grid_for((size_t)n * h * w, 256)), dim3(256), 0, (cudaStream_t)stream, x1, x2, (uint4*)y, n, c, h * w);
+  } else {
+    const size_t total = (size_t)n * h * w * (cpad / 8);
+    tg_launch(pack_pair_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, x1, x2, (uint4*)y, n, c, h, w, cpad / 8, 0, 1);
+  }
   TG_CUDA_LAUNCH_CHECK("pack_pair");
   return TG_OK;
 }

@@ -175,92 +175,6 @@ class SRNet(nn.Module):
         return ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out, accumulate=True)
 
     def conv_layers(self, h, w):
-        """(module, out_h, out_w) per conv, in execution order -- for FRNet.profile."""
-        out = []
-        for name, _, _ in self.ENC:
-            out += [(getattr(self, name)[0], h, w), (getattr(self, name)[2], h, w)]
-            h, w = h // 2, w // 2
-        for name, _, _ in self.DEC:
-            out += [(getattr(self, name)[0], h, w), (getattr(self, name)[2], h, w)]
-            h, w = 2 * h, 2 * w
-        out += [(self.flow[0], h, w), (self.flow[2], h, w)]
-        return out
-
-
-class ResidualBlock(nn.Module):
-    """conv-ReLU-conv + skip (reference tecogan_nets.py:85-100); parameter holder."""
-
-    def __init__(self, nf=64):
-        super().__init__()
-        self.conv = nn.Sequential(nn.Conv2d(nf, nf, 3, 1, 1, bias=True), nn.Identity(),
-                                  nn.Conv2d(nf, nf, 3, 1, 1, bias=True))
-
-
-class SRNet(nn.Module):
-    """Reconstruction + upsampling network (reference tecogan_nets.py:103-147)."""
-
-    def __init__(self, in_nc, out_nc, nf, nb, upsample_func, scale):
-        super().__init__()
-        self.in_nc, self.out_nc, self.nf, self.nb, self.scale = in_nc, out_nc, nf, nb, scale
-        self.conv_in = nn.Sequential(nn.Conv2d((scale ** 2 + 1) * in_nc, nf, 3, 1, 1, bias=True),
-                                     nn.Identity())
-        self.resblocks = nn.Sequential(*[ResidualBlock(nf) for _ in range(nb)])
-        ups = [nn.ConvTranspose2d(nf, nf, 3, 2, 1, output_padding=1, bias=True), nn.Identity()]
-        if scale == 4:
-            ups += [nn.ConvTranspose2d(nf, nf, 3, 2, 1, output_padding=1, bias=True), nn.Identity()]
-        self.conv_up = nn.Sequential(*ups)
-        self.conv_out = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
-        self.upsample_func = upsample_func
-        self._cache = _ConvCache()
-        self._chain = None
-
-    def forward(self, lr_curr, hr_prev_tran):
-        """lr_curr nchw, hr_prev_tran n(s*s*c)hw (both fp32) -> hr nchw fp32"""
-        lr_curr = _cuda_f32(lr_curr, 'lr_curr')
-        x = ops.nchw_to_nhwc(torch.cat([lr_curr, _cuda_f32(hr_prev_tran, 'hr_prev_tran')], dim=1))
-        return self.run_nhwc(x, lr_curr)
-
-    def run_nhwc(self, x, lr_curr, out=None):
-        """x = SRNet input NHWC fp16 [n,h,w,64] (channels [lr_curr | space_to_depth(warp) | 0])."""
-        c = self._cache
-        body = [c.get('in', self.conv_in[0], L.CONV_3X3, _RELU)]
-        for i, blk in enumerate(self.resblocks):
-            body += [c.get(('r', i, 0), blk.conv[0], L.CONV_3X3, _RELU),
-                     c.get(('r', i, 2), blk.conv[2], L.CONV_3X3, L.ACT_NONE)]
-        if (ops.chain_enabled() and ops.default_conv_impl() == 'tcgen05' and x.shape[-1] == 64
-                and ops.ConvChain.supported(body)):
-            # conv_in + all residual blocks in ONE persistent launch: buffers 0 = x (read only),
-            # 1 = block input/output (conv2 writes it in place over its own residual), 2 = conv1 output
-            if self._chain is None or [s[0] for s in self._chain.specs] != body:
-                specs = [(body[0], 0, 1, None)]
-                for i in range(len(self.resblocks)):
-                    specs += [(body[1 + 2 * i], 1, 2, None), (body[2 + 2 * i], 2, 1, 1)]
-                self._chain = ops.ConvChain(specs)
-            a = self._chain([x, torch.empty_like(x), torch.empty_like(x)])
-        else:
-            a = body[0](x)
-            for i in range(len(self.resblocks)):
-                t = body[1 + 2 * i](a)
-                a = body[2 + 2 * i](t, residual=a)
-        ups = [c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU) for u in range(0, len(self.conv_up), 2)]
-        head = c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
-        for up in ups[:-1]:
-            a = up(a)
-        # The last transposed conv writes the largest tensor of the step (n x H x W x 64 fp16 =
-        # 88 MB per frame at 536x1280) and conv_out reads it straight back.  Running the two per
-        # group of frames keeps the intermediate in the 126 MB L2 between producer and consumer.
-        # out = conv_out(a) (pure-store epilogue), then out += upsample_func(lr_curr)
-        n = a.shape[0]
-        chunks = max(1, min(n, ops.tail_chunks()))
-        if out is None:
-            H, W = a.shape[1] * 2, a.shape[2] * 2
-            out = torch.empty((n, self.out_nc, H, W), dtype=torch.float32, device=a.device)
-        for i in range(chunks):
-            lo, hi = n * i // chunks, n * (i + 1) // chunks
-            head(ups[-1](a[lo:hi]), y=out[lo:hi])
-        return ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out, accumulate=True)
-
-    def conv_layers(self, h, w):
         out = [(self.conv_in[0], h, w)]
         for blk in self.resblocks:
             out += [(blk.conv[0], h, w), (blk.conv[2], h, w)]

@@ -306,8 +306,8 @@ def time_kernels(dev, pk):
         out['roofline_warp' if variant == 'hrflow' else 'roofline_warp_fused_lrflow'] = {
             'kernel': f'warp_s2d_concat_kernel<4,{variant}> (4 frames/launch)', 'bound': 'hbm',
             'achieved': alg / t / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': alg / t / 1e9 / pk['hbm_gbs'],
-            # one `ncu --set full` capture of the LR-flow variant (profiles/ncu_warp_r1q.md)
-            'traffic': (36.013312e6 + 0.192256e6) if variant == 'lrflow' else None,
+            # one `ncu --set full` capture of the LR-flow variant (profiles/ncu_warp_r1x.md)
+            'traffic': (36.009728e6 + 0.312576e6) if variant == 'lrflow' else None,
             'us_per_launch': t * 1e6, 'algorithmic_bytes_per_launch': alg,
             'bytes_actually_moved_per_launch': moved, 'moved_gbs': moved / t / 1e9,
             'peak_src': pk['src'], 'how': f'{reps} launches in one CUDA graph, {nb2} rotating buffer sets > L2'}

@@ -215,9 +215,10 @@ def check_conv_vs_simt(a_mode=None, cin=64, cout=64, h=134, w=320, n=1, kind=Non
 def check_conv_chain(n=2, h=37, w=29, blocks=2, max_ctas=0, repeats=1, seed=50):
     """tg_conv_chain_tcgen05 (conv_in + `blocks` residual blocks in ONE persistent launch, tiles
     gated by progress flags) vs the same layers as 1+2*blocks launches of tg_conv_tcgen05 on
-    identical packed weights.  Only the fp32 summation order differs (two partial accumulators),
-    so after each layer's fp16 rounding the two agree to ~1 ulp; `repeats` relaunches on the same
-    workspace exercise the epoch stamping of the flags."""
+    identical packed weights: same MMAs in the same order, so the outputs are bit-identical (the
+    tolerance only guards against a future change of the issue order); `repeats` relaunches on
+    the same workspace exercise the epoch stamping of the flags.  The work buffers are poisoned
+    with NaN so a tile consumed before it was produced cannot go unnoticed."""
     bound = 1.2 / np.sqrt(9 * 64)
     pcs = []
     for i in range(1 + 2 * blocks):
@@ -247,6 +248,27 @@ def check_conv_chain(n=2, h=37, w=29, blocks=2, max_ctas=0, repeats=1, seed=50):
         frac = max(frac, float((d > 0).float().mean()))
         assert e <= 4e-3, f'conv chain vs per-layer launches: rel max {e} (rep {rep}, n={n} h={h} w={w} blocks={blocks})'
     return {'rel_max': worst, 'frac_diff': frac}
+
+
+def check_conv_chain_plain(n=2, h=33, w=50, layers=24, seed=90):
+    """The longest chain the ABI takes (24 layers), no residuals, ping-pong over two work buffers,
+    LeakyReLU between layers -- vs the same layers launched one by one."""
+    bound = 1.4 / np.sqrt(9 * 64)
+    pcs = [ops.PackedConv(rand(seed + 2 * i, 64, 64, 3, 3, lo=-bound, hi=bound).to(DEV),
+                          rand(seed + 2 * i + 1, 64, lo=-0.1, hi=0.1).to(DEV), L.CONV_3X3, L.ACT_LRELU02)
+           for i in range(layers)]
+    specs = [(pcs[i], 0 if i == 0 else 1 + (i - 1) % 2, 1 + i % 2, None) for i in range(layers)]
+    x = nhwc(rand(seed + 200, n, 64, h, w, lo=-1, hi=1), 64)
+    a = x
+    for pc in pcs:
+        a = pc(a)
+    y = ops.ConvChain(specs)([x, torch.full_like(x, float('nan')), torch.full_like(x, float('nan'))])
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    d = (y.float() - a.float()).abs()
+    e = float(d.max() / a.float().abs().max())
+    assert e <= 4e-3, f'24-layer chain vs per-layer launches: rel max {e}'
+    return {'rel_max': e, 'frac_diff': float((d > 0).float().mean())}
 
 
 def check_conv_chain_vs_reference(n=1, h=20, w=24, blocks=1, seed=70):
@@ -551,6 +573,8 @@ CHECKS = {
     'conv_chain_ragged_repeat': lambda: check_conv_chain(n=2, h=37, w=29, blocks=2, repeats=3),
     'conv_chain_few_ctas': lambda: check_conv_chain(n=3, h=50, w=44, blocks=3, max_ctas=5, repeats=2),
     'conv_chain_full': lambda: check_conv_chain(n=4, h=134, w=320, blocks=10, repeats=2),
+    'conv_chain_24_layers': check_conv_chain_plain,
+    'conv_chain_two_tiles_per_cta': lambda: check_conv_chain(n=1, h=134, w=320, blocks=4, max_ctas=0, repeats=2, seed=120),
     'step_golden_g1': lambda: check_step_golden('g1'),
     'step_golden_g15': lambda: check_step_golden('g15'),
     'step_golden_g2_stress': lambda: check_step_golden('g2'),

@@ -189,6 +189,13 @@ int tg_nhwc_f16_to_nchw_f32(const void* x, float* y, int n, int c, int h, int w,
  * x NCHW fp32 [n,c,h,w] -> uint8 [n,h,w,c], round-half-even, clip [0,255] */
 int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int w, void* stream);
 
+/* BD degradation of the data side (codes/utils/data_utils.py:30-53, called on GT frames by
+ * base_model.py:75,115): optional reflect pad by (k-1)/2 | k-1-(k-1)/2, then a depthwise valid
+ * correlation with the k x k kernel `k2d` (device, fp32, = create_kernel(sigma)[0,0]) and stride s.
+ * x NCHW fp32 [n,c,H,W] -> y [n,c,h,w] with h = (Hp-k)/s+1, Hp = H (+k-1 when pad_data). */
+int tg_downsample_bd_nchw_f32(const float* x, const float* k2d, float* y, int n, int c, int H, int W,
+                              int k, int s, int pad_data, void* stream);
+
 /* ------------------------------------------------------------------------
  * Diagnostics: when a device buffer of 16*gridDim uint64 is registered, every
  * tg_conv_tcgen05 launch writes per-CTA role timers (cycles spent by the TMA

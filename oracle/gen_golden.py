@@ -37,12 +37,30 @@ def rand(seed, *shape, lo=0.0, hi=1.0):
     return torch.from_numpy(np.random.default_rng(seed).uniform(lo, hi, size=shape).astype(np.float32))
 
 
+def gen_downsample_bd(data_utils, out_dir):
+    """BD degradation of the data side: create_kernel + downsample_bd
+    (codes/utils/data_utils.py:11-53) -- the reference calls scipy.signal.gaussian, an alias that
+    newer scipy only keeps under scipy.signal.windows."""
+    import scipy.signal
+    if not hasattr(scipy.signal, 'gaussian'):
+        scipy.signal.gaussian = scipy.signal.windows.gaussian
+    kern = data_utils.create_kernel(1.5)                      # [3,3,9,9]
+    a = data_utils.downsample_bd(rand(30, 2, 3, 36, 44), kern, 4, pad_data=True)
+    b = data_utils.downsample_bd(rand(31, 1, 3, 41, 45), kern, 4, pad_data=False)
+    c = data_utils.downsample_bd(rand(32, 1, 3, 27, 30), kern, 2, pad_data=True)
+    np.savez_compressed(os.path.join(out_dir, 'downsample_bd.npz'), kernel=kern.numpy(),
+                        s4_pad=a.numpy(), s4_valid=b.numpy(), s2_pad=c.numpy())
+
+
 def main():
     from oracle.frnet_oracle import make_frnet_params, make_clip
     FRNet, net_utils, data_utils = import_reference()
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(8)
+    gen_downsample_bd(data_utils, out_dir)
+    if sys.argv[1:] == ['bd']:                       # only this fixture
+        return
 
     def ref_model(scale, degradation, seed, gain, nb=10):
         net = FRNet(3, 3, 64, nb, degradation, scale)

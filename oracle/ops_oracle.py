@@ -208,6 +208,38 @@ def float32_to_uint8(x):
 #   cat([lr_curr, space_to_depth(backward_warp(hr_prev, hr_flow), s)], 1)
 #   (tecogan_nets.py:141,247,250)
 # ----------------------------------------------------------------------------
+def create_kernel(sigma, ksize=None):
+    """The 2-D Gaussian of codes/utils/data_utils.py:11-27 as one [k,k] fp32 array (the reference
+    stacks it on the diagonal of a [3,3,k,k] conv weight): k = 1 + 2*int(3*sigma),
+    g[i] = exp(-0.5*((i-(k-1)/2)/sigma)^2) (scipy.signal.windows.gaussian), outer(g,g)/sum."""
+    if ksize is None:
+        ksize = 1 + 2 * int(sigma * 3.0)
+    n = np.arange(ksize, dtype=np.float64) - (ksize - 1.0) / 2.0
+    g = np.exp(-0.5 * (n / float(sigma)) ** 2)
+    k2 = np.outer(g, g)
+    return (k2 / k2.sum()).astype(np.float32)
+
+
+def downsample_bd(data, kernel2d, scale, pad_data):
+    """codes/utils/data_utils.py:30-53: optional reflect pad by (k-1)//2 before / k-1-(k-1)//2 after
+    (F.pad 'reflect'), then a depthwise valid correlation with stride `scale`
+    (F.conv2d(data, block_diag(kernel), stride=scale)).  data [n,c,H,W] fp32 -> [n,c,h,w]."""
+    data = np.asarray(data, dtype=np.float32)
+    k = kernel2d.shape[0]
+    if pad_data:
+        pt = (k - 1) // 2
+        pb = (k - 1) - pt
+        data = np.pad(data, ((0, 0), (0, 0), (pt, pb), (pt, pb)), mode='reflect')
+    H, W = data.shape[2:]
+    oh, ow = (H - k) // scale + 1, (W - k) // scale + 1
+    out = np.zeros(data.shape[:2] + (oh, ow), dtype=np.float64)
+    for i in range(k):
+        for j in range(k):
+            out += np.float64(kernel2d[i, j]) * data[:, :, i:i + (oh - 1) * scale + 1:scale,
+                                                     j:j + (ow - 1) * scale + 1:scale]
+    return out.astype(np.float32)
+
+
 def warp_s2d_concat(hr_prev, hr_flow, lr_curr, scale, exact_reference_grid=True):
     w = backward_warp(hr_prev, hr_flow, exact_reference_grid)
     return np.concatenate([np.asarray(lr_curr, dtype=F32), space_to_depth(w, scale)], axis=1)

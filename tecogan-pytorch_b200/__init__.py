@@ -6,10 +6,11 @@ from .lib import TecoganB200Error, load as load_library, LIB_PATH  # noqa: F401
 from .networks import FRNet, FNet, SRNet, ResidualBlock, BaseSequenceGenerator  # noqa: F401
 from .net_utils import (space_to_depth, backward_warp, get_upsampling_func,  # noqa: F401
                         BicubicUpsampler, BilinearUpsampler)
+from .data_utils import create_kernel, downsample_bd  # noqa: F401
 from .factory import define_generator  # noqa: F401
 from .engine import infer_clips, ClipEngine  # noqa: F401
 from .sharding import clips_for_rank  # noqa: F401
 
 __all__ = ['FRNet', 'FNet', 'SRNet', 'define_generator', 'space_to_depth', 'backward_warp',
            'get_upsampling_func', 'BicubicUpsampler', 'infer_clips', 'ClipEngine',
-           'clips_for_rank', 'load_library', 'TecoganB200Error']
+           'clips_for_rank', 'load_library', 'TecoganB200Error', 'create_kernel', 'downsample_bd']

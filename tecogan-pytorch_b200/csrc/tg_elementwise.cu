@@ -478,6 +478,44 @@ __global__ void to_uint8_c3x4_kernel(const float4* __restrict__ x, uint32_t* __r
   }
 }
 
+// Gaussian blur + subsample of the BD degradation (data_utils.py:30-53).  One CTA = 32 x 8 outputs:
+// the (7s+k) x (31s+k) input patch (reflect-padded when pad_data) is staged in shared memory once,
+// every thread then accumulates its k*k taps from it.
+__global__ void __launch_bounds__(256)
+downsample_bd_kernel(const float* __restrict__ x, const float* __restrict__ k2d, float* __restrict__ y,
+                     int H, int W, int oh, int ow, int k, int s, int pad) {
+  tg_pdl_wait();
+  tg_pdl_trigger();
+  extern __shared__ float bd_smem[];
+  const int tw = 31 * s + k, th = 7 * s + k;
+  float* taps = bd_smem;                 // [k*k]
+  float* tile = bd_smem + k * k;         // [th][tw]
+  const int plane = blockIdx.z;
+  const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * 8;
+  const float* xp = x + (size_t)plane * H * W;
+  for (int i = threadIdx.x; i < k * k; i += 256) taps[i] = __ldg(k2d + i);
+  for (int i = threadIdx.x; i < th * tw; i += 256) {
+    const int ty = i / tw, tx = i - ty * tw;
+    int iy = oy0 * s + ty - pad, ix = ox0 * s + tx - pad;
+    // F.pad(..., 'reflect'): -i -> i, H-1+i -> H-1-i; positions beyond what any valid output of
+    // this tile needs are clamped (never used)
+    iy = iy < 0 ? -iy : (iy >= H ? 2 * (H - 1) - iy : iy);
+    ix = ix < 0 ? -ix : (ix >= W ? 2 * (W - 1) - ix : ix);
+    iy = tg_clampi(iy, 0, H - 1);
+    ix = tg_clampi(ix, 0, W - 1);
+    tile[i] = __ldg(xp + (size_t)iy * W + ix);
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int ox = ox0 + lx, oy = oy0 + ly;
+  if (ox >= ow || oy >= oh) return;
+  float acc = 0.f;
+  const float* t0 = tile + (ly * s) * tw + lx * s;
+  for (int i = 0; i < k; ++i)
+    for (int j = 0; j < k; ++j) acc += taps[i * k + j] * t0[i * tw + j];
+  y[((size_t)plane * oh + oy) * ow + ox] = acc;
+}
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 32;
@@ -538,6 +576,31 @@ int tg_warp_s2d_concat_lrflow(const float* hr_prev, const float* lr_flow, const 
                               int up_mode, int cpad, void* stream) {
   return warp_launch(hr_prev, lr_flow, lr_curr, out, n, c, h, w, h8, w8, s, up_mode, cpad, true,
                      stream);
+}
+
+int tg_downsample_bd_nchw_f32(const float* x, const float* k2d, float* y, int n, int c, int H, int W,
+                              int k, int s, int pad_data, void* stream) {
+  TG_REQUIRE(x && k2d && y, TG_E_INVALID, "downsample_bd: null pointer");
+  TG_REQUIRE(n > 0 && c > 0 && H > 0 && W > 0 && k >= 1 && s >= 1, TG_E_INVALID, "downsample_bd: bad size");
+  TG_REQUIRE(k <= 31 && s <= 8, TG_E_UNSUPPORTED, "downsample_bd: kernel %d / stride %d too large", k, s);
+  const int pad = pad_data ? (k - 1) / 2 : 0;
+  const int Hp = H + (pad_data ? k - 1 : 0), Wp = W + (pad_data ? k - 1 : 0);
+  TG_REQUIRE(Hp >= k && Wp >= k, TG_E_INVALID, "downsample_bd: image smaller than the kernel");
+  TG_REQUIRE(!pad_data || (k - 1 - pad < H && k - 1 - pad < W), TG_E_INVALID,
+             "downsample_bd: reflect padding needs pad < size");
+  const int oh = (Hp - k) / s + 1, ow = (Wp - k) / s + 1;
+  TG_REQUIRE((size_t)n * c <= 65535, TG_E_UNSUPPORTED, "downsample_bd: n*c too large");
+  const size_t smem = ((size_t)k * k + (size_t)(7 * s + k) * (31 * s + k)) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(downsample_bd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  TG_REQUIRE(smem <= 160 * 1024, TG_E_UNSUPPORTED, "downsample_bd: tile does not fit in shared memory");
+  dim3 grid(tg_ceil_div(ow, 32), tg_ceil_div(oh, 8), n * c);
+  tg_launch(downsample_bd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, x, k2d, y, H, W, oh, ow, k, s, pad);
+  TG_CUDA_LAUNCH_CHECK("downsample_bd");
+  return TG_OK;
 }
 
 int tg_maxpool2x2_nhwc_f16(const void* x, void* y, int n, int h, int w, int c, void* stream) {

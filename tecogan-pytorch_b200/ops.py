@@ -323,6 +323,23 @@ def upsample(x, scale, up_mode, out_hw=None, mul=1.0, y=None, accumulate=False):
     return y
 
 
+def downsample_bd(x, k2d, scale, pad_data, y=None):
+    """x NCHW fp32, k2d [k,k] fp32 (device) -> blurred + subsampled NCHW fp32 (tg_downsample_bd_nchw_f32)."""
+    _req(x, torch.float32, 'data', 4)
+    _req(k2d, torch.float32, 'kernel', 2)
+    n, c, H, W = x.shape
+    k = k2d.shape[0]
+    if k2d.shape[1] != k:
+        raise L.TecoganB200Error('downsample_bd: kernel must be square')
+    Hp, Wp = (H + k - 1, W + k - 1) if pad_data else (H, W)
+    oh, ow = (Hp - k) // scale + 1, (Wp - k) // scale + 1
+    if y is None:
+        y = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    L.check(L.load().tg_downsample_bd_nchw_f32(_ptr(x), _ptr(k2d), _ptr(y), n, c, H, W, k, scale,
+                                               1 if pad_data else 0, _stream()), 'tg_downsample_bd')
+    return y
+
+
 def float_to_uint8_nhwc(x, y=None):
     _req(x, torch.float32, 'x', 4)
     n, c, h, w = x.shape

@@ -148,6 +148,27 @@ def check_module_ops():
     return {'warp_abs': float(e_w), 'upsample_abs': float(e_b)}
 
 
+def check_downsample_bd():
+    """tg_downsample_bd_nchw_f32 (through the data_utils drop-in) vs the reference-generated fixture
+    and the oracle, incl. a frame-sized input."""
+    g = np.load(os.path.join(G, 'downsample_bd.npz'))
+    kern = T.create_kernel(1.5)
+    res = {}
+    for name, seed, shape, s, pad in (('s4_pad', 30, (2, 3, 36, 44), 4, True), ('s4_valid', 31, (1, 3, 41, 45), 4, False),
+                                      ('s2_pad', 32, (1, 3, 27, 30), 2, True)):
+        y = T.downsample_bd(rand(seed, *shape).to(DEV), kern, s, pad).cpu().numpy()
+        assert y.shape == g[name].shape, (name, y.shape, g[name].shape)
+        res[name] = float(np.abs(y - g[name]).max())
+        assert res[name] <= 2e-6, f'downsample_bd {name}: max abs {res[name]}'
+    x = rand(33, 1, 3, 536, 1280)
+    y = T.downsample_bd(x.to(DEV), kern, 4, True).cpu().numpy()
+    ref = K.downsample_bd(x.numpy(), K.create_kernel(1.5), 4, True)
+    assert y.shape == (1, 3, 134, 320)
+    res['frame'] = float(np.abs(y - ref).max())
+    assert res['frame'] <= 2e-6
+    return res
+
+
 # =============================================================================== convolutions
 def _conv_ref(x, wt, b, kind, act, residual=None):
     """CPU fp32 reference on fp16-rounded operands."""
@@ -545,6 +566,7 @@ CHECKS = {
     'warp_lrflow_bi2': lambda: check_warp_lrflow(2, 'BI', h=20, w=24),
     'pool_upsample': check_pool_upsample,
     'module_ops': check_module_ops,
+    'downsample_bd': check_downsample_bd,
     'conv_simt_64': lambda: check_conv('simt'),
     'conv_simt_pad': lambda: check_conv('simt', cin=64, cout=64, cin_real=51, cout_real=32, act=L.ACT_LRELU02),
     'conv_simt_convT': lambda: check_conv('simt', kind=L.CONVT_3X3_S2),

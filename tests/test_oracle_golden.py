@@ -56,6 +56,23 @@ def test_ops_against_reference_outputs():
     assert np.abs(ct - g['convt']).max() <= 5e-6
 
 
+def test_downsample_bd_against_reference_outputs():
+    """BD degradation (data_utils.py:11-53): oracle and the package's create_kernel vs the
+    reference-generated fixture."""
+    import tecogan_b200 as T
+    g = np.load(os.path.join(G, 'downsample_bd.npz'))
+    k2 = K.create_kernel(1.5)
+    assert k2.shape == (9, 9)
+    assert np.array_equal(g['kernel'][0, 0], k2) and np.array_equal(g['kernel'][2, 2], k2)
+    assert np.array_equal(T.create_kernel(1.5).numpy(), g['kernel'])
+    rng = lambda seed, *shape: np.random.default_rng(seed).uniform(0, 1, size=shape).astype(np.float32)  # noqa: E731
+    for name, seed, shape, s, pad in (('s4_pad', 30, (2, 3, 36, 44), 4, True), ('s4_valid', 31, (1, 3, 41, 45), 4, False),
+                                      ('s2_pad', 32, (1, 3, 27, 30), 2, True)):
+        out = K.downsample_bd(rng(seed, *shape), k2, s, pad)
+        assert out.shape == g[name].shape
+        assert np.abs(out - g[name]).max() <= 1e-6, name
+
+
 def test_bicubic_kernel_values():
     k = K.bicubic_kernels(4)
     assert np.array_equal(k[0], np.array([0, 1, 0, 0], np.float32))

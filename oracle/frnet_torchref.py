@@ -76,3 +76,41 @@ def step(p, lr_curr, lr_prev, hr_prev, scale, degradation, nb=10):
     pw = lr_curr.size(3) - lr_curr.size(3) // 8 * 8
     hr_flow = scale * upsample(p, F.pad(flow, (0, pw, 0, ph), 'reflect'), scale, degradation)
     return srnet(p, lr_curr, s2d(warp(hr_prev, hr_flow), scale), scale, degradation, nb)
+
+
+def forward_sequence(p, lr_data, scale, degradation, nb=10):
+    """FRNet.forward_sequence (tecogan_nets.py:174-225) with the reference's operators; fully
+    differentiable through PyTorch autograd -- the CPU oracle of the generator BACKWARD
+    (SURVEY.md 8-f1): gradients w.r.t. `p` and `lr_data` are pinned against reference-generated
+    gradients in tests/test_oracle_golden.py."""
+    n, t, c, h, w = lr_data.shape
+    lr_prev = lr_data[:, :-1].reshape(n * (t - 1), c, h, w)
+    lr_curr = lr_data[:, 1:].reshape(n * (t - 1), c, h, w)
+    lr_flow = fnet(p, lr_curr, lr_prev)
+    hr_flow = (scale * upsample(p, lr_flow, scale, degradation)).view(n, t - 1, 2, scale * h, scale * w)
+    hr_prev = srnet(p, lr_data[:, 0], torch.zeros(n, scale * scale * c, h, w, dtype=lr_data.dtype,
+                                                  device=lr_data.device), scale, degradation, nb)
+    hr = [hr_prev]
+    for i in range(1, t):
+        hr_prev = srnet(p, lr_data[:, i], s2d(warp(hr_prev, hr_flow[:, i - 1]), scale), scale, degradation, nb)
+        hr.append(hr_prev)
+    return {'hr_data': torch.stack(hr, 1), 'hr_flow': hr_flow, 'lr_prev': lr_prev, 'lr_curr': lr_curr,
+            'lr_flow': lr_flow}
+
+
+def sequence_loss_and_grads(p, lr_data, scale, degradation, seed, nb=10):
+    """loss = <hr_data, R1> + 0.05 <lr_flow, R2> with seeded uniform(-1,1) R1, R2; returns the loss
+    and the gradients w.r.t. every floating-point parameter and lr_data (the protocol of the
+    `fwd_seq_grads_*` fixture, oracle/gen_golden.py)."""
+    import numpy as np
+    q = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith('kernels')) for k, v in p.items()}
+    x = lr_data.clone().requires_grad_(True)
+    d = forward_sequence(q, x, scale, degradation, nb)
+    rng = np.random.default_rng(seed)
+    r1 = torch.from_numpy(rng.uniform(-1, 1, size=tuple(d['hr_data'].shape)).astype(np.float32))
+    r2 = torch.from_numpy(rng.uniform(-1, 1, size=tuple(d['lr_flow'].shape)).astype(np.float32))
+    loss = (d['hr_data'] * r1).sum() + 0.05 * (d['lr_flow'] * r2).sum()
+    names = [k for k, v in q.items() if v.requires_grad]
+    grads = torch.autograd.grad(loss, [q[k] for k in names] + [x])
+    return loss.detach(), dict(zip(names, grads[:-1])), grads[-1]
+

@@ -52,6 +52,31 @@ def gen_downsample_bd(data_utils, out_dir):
                         s4_pad=a.numpy(), s4_valid=b.numpy(), s2_pad=c.numpy())
 
 
+GRAD_FULL = ('fnet.encoder1.0.weight', 'fnet.flow.2.weight', 'fnet.flow.2.bias', 'srnet.conv_in.0.weight',
+             'srnet.resblocks.1.conv.2.bias', 'srnet.conv_up.2.bias', 'srnet.conv_out.weight', 'srnet.conv_out.bias')
+
+
+def gen_sequence_grads(FRNet, out_dir):
+    from oracle.frnet_oracle import make_frnet_params
+    net = FRNet(3, 3, 64, 2, 'BD', 4)
+    net.load_state_dict(make_frnet_params(15, nb=2, scale=4, degradation='BD', gain=1.5), strict=True)
+    net.train()
+    lr_data = rand(9, 1, 3, 3, 16, 16).requires_grad_(True)
+    d = net.forward_sequence(lr_data)
+    rng = np.random.default_rng(16)
+    r1 = torch.from_numpy(rng.uniform(-1, 1, size=tuple(d['hr_data'].shape)).astype(np.float32))
+    r2 = torch.from_numpy(rng.uniform(-1, 1, size=tuple(d['lr_flow'].shape)).astype(np.float32))
+    loss = (d['hr_data'] * r1).sum() + 0.05 * (d['lr_flow'] * r2).sum()
+    loss.backward()
+    named = dict(net.named_parameters())
+    out = {'loss': np.float32(loss.item()), 'd_lr_data': lr_data.grad.numpy(),
+           'names': np.array(list(named)), 'norms': np.array([float(v.grad.norm()) for v in named.values()], np.float64)}
+    for k in GRAD_FULL:
+        out['g:' + k] = named[k].grad.numpy()
+    np.savez_compressed(os.path.join(out_dir, 'fwd_seq_grads_bd4_16x16_nb2_g15.npz'), **out)
+    print('sequence grads: loss', loss.item(), 'max |d lr_data|', float(lr_data.grad.abs().max()))
+
+
 def main():
     from oracle.frnet_oracle import make_frnet_params, make_clip
     FRNet, net_utils, data_utils = import_reference()
@@ -61,6 +86,8 @@ def main():
     gen_downsample_bd(data_utils, out_dir)
     if sys.argv[1:] == ['bd']:                       # only this fixture
         return
+    if sys.argv[1:] == ['grads']:
+        return gen_sequence_grads(FRNet, out_dir)
 
     def ref_model(scale, degradation, seed, gain, nb=10):
         net = FRNet(3, 3, 64, nb, degradation, scale)
@@ -107,6 +134,11 @@ def main():
         d = net.forward_sequence(lr_data)
     np.savez_compressed(os.path.join(out_dir, 'fwd_seq_bd4_16x16_g15.npz'),
                         **{k: v.numpy() for k, v in d.items()})
+
+    # ---- 4b. gradients of forward_sequence (generator backward), nb=2 to keep it small:
+    # loss = <hr_data, R1> + 0.05 <lr_flow, R2>; stored: loss, d/d lr_data, a few whole parameter
+    # gradients and the L2 norm of every parameter gradient
+    gen_sequence_grads(FRNet, out_dir)
 
     # ---- 5. functional ops
     x = rand(20, 2, 3, 20, 24)

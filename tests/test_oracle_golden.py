@@ -121,6 +121,26 @@ def test_forward_sequence():
         assert relerr(d[k].numpy(), g[k]) <= 3e-5, k
 
 
+def test_sequence_gradients_against_reference():
+    """Oracle of the generator BACKWARD: autograd through the torch port
+    of forward_sequence vs gradients the reference itself produced (loss.backward() through
+    FRNet.forward_sequence, oracle/gen_golden.py): loss, d/d lr_data, eight whole parameter
+    gradients and the norm of all 44."""
+    from oracle import frnet_torchref as R
+    g = np.load(os.path.join(G, 'fwd_seq_grads_bd4_16x16_nb2_g15.npz'))
+    p = O.make_frnet_params(15, nb=2, scale=4, degradation='BD', gain=1.5)
+    loss, grads, gx = R.sequence_loss_and_grads(p, rand(9, 1, 3, 3, 16, 16), 4, 'BD', 16, nb=2)
+    assert abs(float(loss) - float(g['loss'])) <= 1e-4 * abs(float(g['loss']))
+    assert relerr(gx.numpy(), g['d_lr_data']) <= 1e-5
+    names = [str(k) for k in g['names']]
+    assert sorted(names) == sorted(grads)
+    for k, nrm in zip(names, g['norms']):
+        assert abs(float(grads[k].norm()) - nrm) <= 1e-4 * max(nrm, 1e-9), k
+    for k in g.files:
+        if k.startswith('g:'):
+            assert relerr(grads[k[2:]].numpy(), g[k]) <= 1e-5, k
+
+
 def test_state_dict_layout_matches_reference_counts():
     # SURVEY.md section 9: BD 4x = 78 entries (76 params + 2 kernels buffers); BI 4x = 76
     assert len(O.frnet_param_shapes(scale=4, degradation='BD')) == 78

@@ -123,8 +123,10 @@ int tg_conv_simt(const tg_conv_desc* d, void* stream);
  *   sync_ws : device memory of tg_conv_chain_workspace_bytes(n,h,w) bytes, zeroed ONCE by the
  *       caller before first use, then owned by the library (epoch-stamped; one chain launch in
  *       flight per workspace).
- * Needs every CTA co-resident (grid = min(#SM, tiles), 1 CTA/SM): do not run it under an SM
- * partition smaller than the device (waits are bounded and trap instead of hanging).
+ * Needs every CTA co-resident (grid = min(#SM, tiles), 1 CTA/SM): launch at most ONE chain at a
+ * time per device (two chains racing for SMs from different streams can starve each other) and
+ * do not run it under an SM partition smaller than the device (waits are bounded and trap
+ * instead of hanging).
  * ---------------------------------------------------------------------- */
 typedef struct tg_chain_layer {
   const void* x;        /* NHWC fp16 [n,h,w,64]                          */

@@ -2,7 +2,8 @@
 // implicit GEMM for sm_100a.
 //
 //   M tile  = 128 output pixels = a 16x8 patch of one image (TMEM lane m <-> pixel (m>>3, m&7))
-//   N       = cout (16 / 64 / 128 / 256), one UMMA covers the whole N
+//   N       = 64 output channels per CTA (layers with 128 / 256 are split over 2 / 4 CTAs); 48 for
+//             the thin heads (MODE_TAPN: 9 taps x 4 couts in N, 3x3 shift-add in the epilogue)
 //   K       = 64-channel chunks x 9 taps; UMMA K = 16 -> 4 MMAs per (tap, chunk)
 //   A       : NHWC fp16 activations, fetched by TMA (4-D tiled map, 128B swizzle, OOB zero fill =
 //             the conv's zero padding) either as ONE halo box (18x10 px) per (tile, chunk) whose
@@ -11,12 +12,14 @@
 //   B       : weights pre-packed on the device in the exact swizzled smem image
 //             (tg_pack_*_weights), either resident in smem for the whole kernel (SRNet, thin
 //             FNet layers) or streamed per (tap, chunk) with cp.async.bulk (fat FNet layers).
-//   D       : fp32 accumulators in TMEM, up to 8 buffers in flight (the epilogue of tile i overlaps
-//             the MMAs of tiles i+1..).  The transposed conv keeps 4 parity accumulators (1/2/2/4 taps) and
-//             stores them through 4 strided tensor maps = the pixel-shuffle interleave.
-//   roles   : warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator,
-//             warps 4..11 = two epilogue groups alternating tiles (tcgen05.ld -> bias/act/residual
-//             -> fp16 -> 128-byte NHWC row straight to global; or the thin-head TAPN epilogues).
+//   D       : fp32 accumulators in TMEM, up to 8 tile buffers in flight (the epilogue of tile i
+//             overlaps the MMAs of tiles i+1..).  The transposed conv keeps 4 parity accumulators
+//             (1/2/2/4 taps); each epilogue thread stores its pixel's 2x2 outputs (pixel shuffle).
+//   roles   : warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane; HALO convs issue two
+//             tiles interleaved, thin heads four), warp 2 = TMEM allocator, warps 4.. = 2 epilogue
+//             groups of 4 warps (4 groups for the transposed conv and the thin heads) taking tiles
+//             round-robin: tcgen05.ld -> bias/act/residual -> fp16 -> the pixel's 128-byte NHWC
+//             row straight to global with 256-bit stores; or the thin-head TAPN epilogues.
 //
 // Replaces the nn.Conv2d / nn.ConvTranspose2d library calls K1, K10, K11, K12 of SURVEY.md 2.1.
 #include <cuda.h>

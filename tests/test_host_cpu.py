@@ -181,3 +181,30 @@ def test_clip_sharding_world_size_2_gloo():
         assert sorted(gathered[0] + gathered[1]) == list(range(7))      # disjoint cover
         assert set(gathered[0]).isdisjoint(gathered[1])
         assert frames == 70.0 and elapsed == 2.0                         # sum of work, max of time
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` is the arm the driver times beside ours; it runs on the host cores
+    (no GPU needed) and must print ONE JSON line with the contract's keys; under torchrun only rank 0
+    works and prints."""
+    import json
+    import subprocess
+    env = dict(os.environ)
+    env.pop('RANK', None)
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+              'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    # a non-zero rank exits 0 without work or output
+    env.update(RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    out = subprocess.run(cmd[:-4] + ['--gpus', '2', '--steps', '1', '--warmup', '1'], capture_output=True, text=True,
+                         timeout=120, env=env, cwd=ROOT)
+    assert out.returncode == 0 and out.stdout.strip() == ''

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- HR frames/sec of the FRNet hot path at 4x BD, LR 3x134x320 -> HR 3x536x1280.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|eager-gpu]
 
 Workload (BASELINE.json configs[1]): TecoGAN 4x BD inference, synthetic 3x134x320 clips, 4 clips
 lock-stepped per GPU.  One "step" = one recurrent frame of all 4 clips on one GPU = 4 HR frames.
@@ -14,12 +14,17 @@ Prints ONE JSON line (rank 0):
   e2e        the same metric through the reference-facing call FRNet.infer_sequence() with HOST
              buffers: per step the H2D copy of the LR frames and the D2H copy of the uint8 HR
              frames are inside the timed region
-  roofline   the dominant kernel (SRNet 64->64 3x3 conv, tcgen05) timed live with CUDA events
-  roofline_warp  the fused warp+space_to_depth+concat kernel against the HBM roofline
+  roofline   the dominant kernel (conv_chain_kernel: SRNet conv_in + 10 residual blocks = 21 convs
+             64->64 in one persistent tcgen05 launch) timed live with CUDA events against the measured
+             tensor peak; `traffic` = its DRAM bytes from one ncu --set full capture
+  roofline_conv_single  one residual conv 64->64 as its own launch (conv_tcgen05_kernel)
+  roofline_warp*  the fused warp+space_to_depth+concat kernel against the HBM roofline
   cpu_baseline   the reference's CPU path (oracle/frnet_torchref.py: same PyTorch CPU library
              ops as the reference) on the box's host cores, bounded sample (rank 0, N=1)
 
 --impl reference times ONLY that CPU path with the same metric/unit (rank 0 alone).
+--impl eager-gpu (context, not part of the contract) runs the reference's operator sequence on
+PyTorch's CUDA library kernels on the same GPU.
 """
 import argparse
 import json

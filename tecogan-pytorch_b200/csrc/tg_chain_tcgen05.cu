@@ -147,9 +147,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   const uint32_t bar_wfull = base + 256;          // [9] tap t of the current layer's weights landed
   const uint32_t bar_wfree = base + 336;          // [9] every MMA of the layer that reads tap t retired
   const uint32_t bar_wstart = base + 416;         // [1] the MMA issuer has taken delivery of a layer's weights
-  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 424);
-  volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 428);
-  const uint32_t deps_ok_addr = base + 432;       // tiles (in this CTA's sequence) whose dependencies are verified
+  const uint32_t bar_wearly = base + 424;         // [1] the streamer is past its waits for the next layer's early taps
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 432);
+  volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 436);
+  const uint32_t deps_ok_addr = base + 440;       // tiles (in this CTA's sequence) whose dependencies are verified
   float* bias_s = reinterpret_cast<float*>(sm + kOffBias);
   const uint32_t smem_w0 = base + kOffW;
   const uint32_t smem_stage0 = base + kOffStage;
@@ -169,6 +170,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     for (int i = 0; i < kBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
     for (int i = 0; i < 9; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 1); }
     mbar_init(bar_wstart, 1);
+    mbar_init(bar_wearly, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
@@ -190,7 +192,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   for (int i = threadIdx.x; i < L * 64; i += kThreads) bias_s[i] = cp.layers[i >> 6].bias[i & 63];
   if (threadIdx.x == 0) {
     *epoch_s = ld_acquire_gpu(cp.sync);
-    *reinterpret_cast<volatile uint32_t*>(sm + 432) = (uint32_t)n_my;   // layer 0 has no dependencies
+    *reinterpret_cast<volatile uint32_t*>(sm + 440) = (uint32_t)n_my;   // layer 0 has no dependencies
   }
   __syncthreads();
   const uint32_t fbase = (*epoch_s) << 5;              // flags of this launch: fbase + layers done
@@ -280,6 +282,13 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         __syncwarp();
         if (timing) t_bd += clock64() - tb0;
       }
+      if (hand_over) {
+        // This tile completes the hand-over barriers of layer l.  The streamer waits on the PREVIOUS
+        // completion of wfree[4..8] (for the next layer's taps 0-4, which reuse layer l-1's slots): it
+        // must be past those waits first, or a late streamer would find the barriers two phases ahead
+        // (found by tests/test_chain_protocol_model.py; needs one tile per CTA and layer to happen).
+        mbar_wait(bar_wearly, (uint32_t)l & 1u, 10);
+      }
       // The 36 MMAs are issued in two parts (taps 0-3 | taps 4-8).  On the last tile of a layer a
       // commit behind each part hands those taps' ring slots back to the weight streamer.
 #pragma unroll
@@ -356,6 +365,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
           mbar_expect_tx(bar_wfull + 8 * t, kTapWBytes);
           bulk_load(smem_w0 + (uint32_t)(gi % kSlots) * kTapWBytes, cp.layers[l].w + (size_t)t * kTapWBytes,
                     kTapWBytes, bar_wfull + 8 * t);
+          if (t == kSlots - 9 - 1) mbar_arrive(bar_wearly);   // every wait that refers to layer l-2 is behind us
         }
       }
     }

@@ -313,7 +313,7 @@ SHAPES = [
 
 @pytest.mark.parametrize('shape', SHAPES)
 def test_chain_protocol_random_schedules(shape):
-    for seed in range(6):
+    for seed in range(16):
         Sim(*shape, seed=seed).run()
 
 

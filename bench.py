@@ -23,8 +23,9 @@ Prints ONE JSON line (rank 0):
              ops as the reference) on the box's host cores, bounded sample (rank 0, N=1)
 
 --impl reference times ONLY that CPU path with the same metric/unit (rank 0 alone).
---impl eager-gpu (context, not part of the contract) runs the reference's operator sequence on
-PyTorch's CUDA library kernels on the same GPU.
+--impl eager-gpu is a second REFERENCE arm (context, not part of the contract, never what `value`
+measures): the same port of the reference's operator sequence, executed by PyTorch's CUDA library
+kernels on the same GPU instead of the host cores.
 """
 import argparse
 import json

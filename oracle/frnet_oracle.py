@@ -166,68 +166,6 @@ def frnet_forward_sequence(p, lr_data, scale, degradation):
     }
 
 
-# ----------------------------------------------------------------------------
-# deterministic weights with the reference's state_dict layout
-# ----------------------------------------------------------------------------
-def frnet_param_shapes(in_nc=3, out_nc=3, nf=64, nb=10, scale=4, degradation='BD'):
-    shapes = OrderedDict()
-
-    def conv(name, cin, cout):
-        shapes[name + '.weight'] = (cout, cin, 3, 3)
-        shapes[name + '.bias'] = (cout,)
-
-    if degradation == 'BD':
-        shapes['upsample_func.kernels'] = (scale, 4)
-    chans = [('encoder1', 2 * in_nc, 32, 32), ('encoder2', 32, 64, 64), ('encoder3', 64, 128, 128),
-             ('decoder1', 128, 256, 256), ('decoder2', 256, 128, 128), ('decoder3', 128, 64, 64)]
-    for nm, a, b, c2 in chans:
-        conv(f'fnet.{nm}.0', a, b)
-        conv(f'fnet.{nm}.2', b, c2)
-    conv('fnet.flow.0', 64, 32)
-    conv('fnet.flow.2', 32, 2)
-    conv('srnet.conv_in.0', (scale * scale + 1) * in_nc, nf)
-    for i in range(nb):
-        conv(f'srnet.resblocks.{i}.conv.0', nf, nf)
-        conv(f'srnet.resblocks.{i}.conv.2', nf, nf)
-    for u in range(2 if scale == 4 else 1):
-        shapes[f'srnet.conv_up.{2 * u}.weight'] = (nf, nf, 3, 3)  # ConvT: [Cin,Cout,kH,kW]
-        shapes[f'srnet.conv_up.{2 * u}.bias'] = (nf,)
-    conv('srnet.conv_out', nf, out_nc)
-    if degradation == 'BD':
-        shapes['srnet.upsample_func.kernels'] = (scale, 4)
-    return shapes
-
-
-def make_frnet_params(seed=0, in_nc=3, out_nc=3, nf=64, nb=10, scale=4, degradation='BD',
-                      gain=1.0):
-    """Seeded weights, U(-b, b) with b = gain/sqrt(fan_in) like PyTorch's default
-    conv init (what codes/main.py:227-228 profiles with; no checkpoint is loaded).
-    numpy PCG64 stream -> identical on every box."""
-    rng = np.random.default_rng(seed)
-    p = OrderedDict()
-    for name, shp in frnet_param_shapes(in_nc, out_nc, nf, nb, scale, degradation).items():
-        if name.endswith('kernels'):
-            p[name] = _t(K.bicubic_kernels(scale))
-            continue
-        if name.endswith('.weight'):
-            if 'conv_up' in name:
-                fan_in = shp[1] * 9   # torch computes fan_in from dim 1 for ConvTranspose2d
-            else:
-                fan_in = shp[1] * 9
-            last_fan_in = fan_in
-        else:
-            fan_in = last_fan_in
-        b = gain / np.sqrt(fan_in)
-        p[name] = _t(rng.uniform(-b, b, size=shp).astype(np.float32))
-    return p
-
-
-def make_clip(seed, t, c, h, w, shift=1):
-    """Smooth translating pattern: bicubic-upsampled seeded noise
-    shifted `shift` px per frame, values in [0,1]."""
-    rng = np.random.default_rng(seed)
-    gh, gw = h // 4 + 4, (w + shift * t) // 4 + 4
-    base = rng.uniform(0.0, 1.0, size=(1, c, gh, gw)).astype(np.float32)
-    big = np.clip(K.bicubic_upsample(base, 4), 0.0, 1.0)
-    frames = [big[0, :, 2:2 + h, 2 + shift * i:2 + shift * i + w] for i in range(t)]
-    return _t(np.stack(frames).astype(np.float32))
+# seeded weight / clip generators live in the neutral top-level module `synthetic` (bench.py and the
+# product smoke path must not import oracle/ for their inputs); re-exported for the tests
+from synthetic import frnet_param_shapes, make_frnet_params, make_clip  # noqa: E402,F401

@@ -657,14 +657,12 @@ int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int
   for (int i = n_maps; i < kMaxMaps; ++i) p.maps[i] = p.maps[0];
   for (int l = n_layers; l < TG_CHAIN_MAX_LAYERS; ++l) p.layers[l] = p.layers[0];
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
+  static TgPerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
     cudaError_t e = cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e != cudaSuccess) attr_err = e;
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_chain: cudaFuncSetAttribute: %s",
              cudaGetErrorString(attr_err));
@@ -672,12 +670,36 @@ int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int
   int sms = 0;
   int rc = tg_device_sm_count(&sms);
   if (rc != TG_OK) return rc;
-  // every CTA must be resident at once (tiles wait on tiles of other CTAs): one CTA per SM at most
-  int grid = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;
+  // Every CTA must be resident at once (tiles wait on tiles of other CTAs).  Two guards:
+  //  (1) the grid never exceeds what the occupancy calculator says fits on this device / partition;
+  //  (2) the launch is COOPERATIVE, so the driver only starts the grid when all of its CTAs can be
+  //      co-scheduled -- a second chain on another stream, an MPS client or a green-context SM
+  //      partition delays or fails the launch instead of dead-locking it into the watchdog trap.
+  // TECOGAN_B200_CHAIN_COOP=0 restores the plain PDL launch (A/B measurements on a whole GPU only).
+  int per_sm = 0;
+  cudaError_t oerr = p.dbg ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_chain_kernel<true>, kThreads, kSmemBytes)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_chain_kernel<false>, kThreads, kSmemBytes);
+  TG_REQUIRE(oerr == cudaSuccess, (int)oerr, "conv_chain: occupancy query: %s", cudaGetErrorString(oerr));
+  TG_REQUIRE(per_sm >= 1, TG_E_UNSUPPORTED, "conv_chain: kernel does not fit on an SM of this device");
+  int grid = (max_ctas > 0 && max_ctas < sms) ? max_ctas : sms;     // 1 CTA per SM (512 TMEM columns each)
   if (grid > p.num_tiles) grid = p.num_tiles;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t lerr = p.dbg ? tg_launch(conv_chain_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p)
-                           : tg_launch(conv_chain_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p);
+  static int coop = -1;
+  if (coop < 0) {
+    const char* e = getenv("TECOGAN_B200_CHAIN_COOP");
+    coop = (e != nullptr && e[0] == '0') ? 0 : 1;
+    int dev = 0, can = 0;
+    if (coop && (cudaGetDevice(&dev) != cudaSuccess ||
+                 cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !can))
+      coop = 0;
+  }
+  cudaError_t lerr;
+  if (coop)
+    lerr = p.dbg ? tg_launch_cooperative(conv_chain_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p)
+                 : tg_launch_cooperative(conv_chain_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p);
+  else
+    lerr = p.dbg ? tg_launch(conv_chain_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, st, p)
+                 : tg_launch(conv_chain_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, st, p);
   TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "conv_chain: launch failed: %s", cudaGetErrorString(lerr));
   TG_CUDA_LAUNCH_CHECK("conv_chain");
   return TG_OK;

@@ -56,7 +56,39 @@ static inline cudaError_t tg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
   cfg.numAttrs = tg_pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+
+// Cooperative launch: the driver schedules the grid only when EVERY CTA can be resident at once
+// (or fails the launch) -- required by kernels whose CTAs wait on each other (conv_chain_kernel).
+// Not combined with programmatic dependent launch: such a kernel starts after its predecessor.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tg_launch_cooperative(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                                cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif
+
+// cudaFuncSetAttribute is per DEVICE: run `fn` once for every device this process launches on.
+struct TgPerDeviceOnce {
+  int done[64] = {};
+  cudaError_t err[64] = {};
+  template <typename F>
+  cudaError_t run(F fn) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fn();
+    if (!done[dev]) { err[dev] = fn(); done[dev] = 1; }
+    return err[dev];
+  }
+};
 
 // ---------------------------------------------------------------- packed-weight geometry
 // One weight tile = [cout_pad rows][64 k] fp16, 128-byte rows, 128B swizzle:

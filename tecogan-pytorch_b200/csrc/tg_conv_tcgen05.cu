@@ -748,20 +748,20 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
                    (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
   if (rc != TG_OK) return rc;
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    cudaError_t e;
+  static TgPerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    cudaError_t e, err = cudaSuccess;
 #define TG_SET_ATTR(K, H)                                                                                 \
     e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)kSmemLimit);                                                            \
-    if (e != cudaSuccess) attr_err = e;                                                                   \
+    if (e != cudaSuccess) err = e;                                                                        \
     e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                              (int)kSmemLimit);                                                            \
-    if (e != cudaSuccess) attr_err = e;
+    if (e != cudaSuccess) err = e;
     TG_SET_ATTR(TG_CONV_3X3, MODE_HALO) TG_SET_ATTR(TG_CONV_3X3, MODE_TAP) TG_SET_ATTR(TG_CONV_3X3, MODE_TAPN)
     TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_HALO) TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_TAP)
 #undef TG_SET_ATTR
+    return err;
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_tcgen05: cudaFuncSetAttribute: %s",
              cudaGetErrorString(attr_err));
@@ -772,6 +772,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   int grid = d->max_ctas > 0 ? d->max_ctas : sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
   grid -= grid % p.n_split;             // every CTA keeps one fixed N slice (resident weights)
+  if (grid < p.n_split) grid = p.n_split;
   // always request the full carve-out: exactly one CTA per SM, so the 512-column TMEM
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;

@@ -3,6 +3,8 @@
 // Reference call sites are cited per entry point in include/tecogan_b200.h.
 #include "tg_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 // =====================================================================================
@@ -34,15 +36,20 @@ __device__ __forceinline__ float bilerp_border(const float* __restrict__ plane, 
 }
 
 // One CTA = RY LR rows x LRW=128/S LR pixels; 128 threads, thread t owns HR column X = x0*S + t and
-// walks the S HR rows of each LR row (S*RY pixels per thread -> enough independent gathers in
-// flight per thread, few CTAs -> little launch overhead).
+// walks the S HR rows of each LR row in passes of SP rows (SP*12 independent gathers in flight per
+// thread; SP = 2 keeps the kernel at <= 64 registers -> 8 CTAs = 32 warps per SM, twice the bytes in
+// flight per SM of the SP = S version that ncu showed latency-bound at 29 % occupancy).
 //   LRFLOW: the LR flow neighbourhood ((RY+3) rows x LRW+3 cols, reflect-padded + replicate-clamped)
 //   is staged in smem once; each thread evaluates the x-pass of the separable 4-tap upsampler for its
 //   own column into registers (RY+3 values per component) and the y-pass per HR row.
 //   FLOW: 0 = HR flow given; 1 / 2 = LR flow, upsampled inline with the bicubic / bilinear
 //   upsample_func (compile time, so the y-pass taps are immediates).
-template <int S, int FLOW, int RY>
-__global__ void __launch_bounds__(128)
+//   The NHWC transpose goes through a shared-memory tile whose pixel stride is cpad*2 + 16 bytes:
+//   with the natural 128-byte stride the 8 LR pixels of a warp hit the same bank (8-way conflict on
+//   every 2-byte store -- the top stall of the round-1 capture); +16 B spreads them over all banks
+//   and keeps the 16-byte alignment of the vector read-out.
+template <int S, int FLOW, int RY, int SP>
+__global__ void __launch_bounds__(128, SP == S ? 5 : 8)
 warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                        const float* __restrict__ lr_curr, __half* __restrict__ out, int C, int h,
                        int w, int h8, int w8, int cpad) {
@@ -54,7 +61,8 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
   constexpr int FW = LRW + 3;                 // LR columns x0-1 .. x0+LRW+1
   constexpr int FH = RY + 3;                  // LR rows    y0-1 .. y0+RY+1
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* tile = reinterpret_cast<__half*>(smem_raw);  // [LRW][cpad]
+  const int tstride = cpad + 8;               // halves per tile pixel (cpad*2 + 16 bytes)
+  __half* tile = reinterpret_cast<__half*>(smem_raw);  // [LRW][tstride]
   __shared__ float fsrc[LRFLOW ? 2 * FH * FW : 1];     // [comp][row][col]
 
   const int t = threadIdx.x;
@@ -66,7 +74,7 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
   const int lx = t / S, sx = t - lx * S;
 
   // the pad channels [(S*S+1)*C, cpad) are never written again: zero the whole tile once
-  for (int i = t; i < LRW * cpad / 8; i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = t; i < LRW * tstride / 8; i += 128) reinterpret_cast<uint4*>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
 
   float hx[2][FH];                      // x-pass of the flow upsampler, this thread's column
   if (LRFLOW) {
@@ -100,77 +108,80 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
       const int xx = x0 + p;
       float v = 0.f;
       if (xx < w) v = __ldg(lr_curr + (((size_t)n * C + k) * h + y) * w + xx);
-      tile[p * cpad + k] = __float2half(v);
+      tile[p * tstride + k] = __float2half(v);
     }
     if (X < W) {
-      float u[S], v[S];
-      if (LRFLOW) {
 #pragma unroll
-        for (int sy = 0; sy < S; ++sy) {
-          float ky[4];
-          tg_up_taps(up_mode, sy, S, ky);
-          u[sy] = (float)S * (ky[0] * hx[0][ry] + ky[1] * hx[0][ry + 1] + ky[2] * hx[0][ry + 2] + ky[3] * hx[0][ry + 3]);
-          v[sy] = (float)S * (ky[0] * hx[1][ry] + ky[1] * hx[1][ry + 1] + ky[2] * hx[1][ry + 2] + ky[3] * hx[1][ry + 3]);
-        }
-      } else {
-        const float* f0 = flow + (((size_t)n * 2 + 0) * H + (size_t)y * S) * W + X;
-        const float* f1 = flow + (((size_t)n * 2 + 1) * H + (size_t)y * S) * W + X;
+      for (int s0 = 0; s0 < S; s0 += SP) {
+        float u[SP], v[SP];
+        if (LRFLOW) {
 #pragma unroll
-        for (int sy = 0; sy < S; ++sy) {
-          u[sy] = __ldg(f0 + (size_t)sy * W);
-          v[sy] = __ldg(f1 + (size_t)sy * W);
-        }
-      }
-      if (C == 3) {
-        // two-phase gather: compute the 4 corner offsets of all S pixels, issue all 12*S loads,
-        // then combine -- 12*S independent loads in flight per thread hide the L2/DRAM latency
-        int o00[S];
-        float ax[S], ay[S];
-#pragma unroll
-        for (int sy = 0; sy < S; ++sy) {
-          float fx = (float)X + u[sy];
-          float fy = (float)(y * S + sy) + v[sy];
-          fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
-          fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
-          // The four corners are (ya,xa),(ya,xa+1),(ya+1,xa),(ya+1,xa+1) with xa <= W-2, ya <= H-2:
-          // at the far border (fx == W-1) the pair is shifted one to the left and the fraction
-          // becomes 1, which selects the same sample with weight exactly 1 (bit-identical result,
-          // net_utils.py:76 padding_mode='border') -- and the corner addresses are immediates of
-          // two base addresses instead of four independent ones.
-          const int xa = min((int)floorf(fx), W - 2), ya = min((int)floorf(fy), H - 2);
-          ax[sy] = fx - (float)xa; ay[sy] = fy - (float)ya;
-          o00[sy] = ya * W + xa;
-        }
-        float g[S][3][4];
-        const float* img = hr_prev + (size_t)n * 3 * H * W;
-#pragma unroll
-        for (int sy = 0; sy < S; ++sy)
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const float* r0 = img + (size_t)k * H * W + o00[sy];
-            const float* r1 = r0 + W;
-            g[sy][k][0] = __ldg(r0); g[sy][k][1] = __ldg(r0 + 1);
-            g[sy][k][2] = __ldg(r1); g[sy][k][3] = __ldg(r1 + 1);
+          for (int j = 0; j < SP; ++j) {
+            float ky[4];
+            tg_up_taps(up_mode, s0 + j, S, ky);
+            u[j] = (float)S * (ky[0] * hx[0][ry] + ky[1] * hx[0][ry + 1] + ky[2] * hx[0][ry + 2] + ky[3] * hx[0][ry + 3]);
+            v[j] = (float)S * (ky[0] * hx[1][ry] + ky[1] * hx[1][ry + 1] + ky[2] * hx[1][ry + 2] + ky[3] * hx[1][ry + 3]);
           }
+        } else {
+          const float* f0 = flow + (((size_t)n * 2 + 0) * H + (size_t)y * S + s0) * W + X;
+          const float* f1 = flow + (((size_t)n * 2 + 1) * H + (size_t)y * S + s0) * W + X;
 #pragma unroll
-        for (int sy = 0; sy < S; ++sy) {
-          // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
-          __half* dst = tile + lx * cpad + 3 + (sy * S + sx) * 3;
-          const float w00 = (1.f - ax[sy]) * (1.f - ay[sy]), w01 = ax[sy] * (1.f - ay[sy]);
-          const float w10 = (1.f - ax[sy]) * ay[sy], w11 = ax[sy] * ay[sy];
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            dst[k] = __float2half(g[sy][k][0] * w00 + g[sy][k][1] * w01 + g[sy][k][2] * w10 + g[sy][k][3] * w11);
+          for (int j = 0; j < SP; ++j) {
+            u[j] = __ldg(f0 + (size_t)j * W);
+            v[j] = __ldg(f1 + (size_t)j * W);
+          }
         }
-      } else {
+        if (C == 3) {
+          // two-phase gather: compute the corner offsets of the SP pixels, issue all 12*SP loads,
+          // then combine -- independent loads in flight per thread hide the L2/DRAM latency
+          int o00[SP];
+          float ax[SP], ay[SP];
 #pragma unroll
-        for (int sy = 0; sy < S; ++sy) {
-          const float fx = (float)X + u[sy];
-          const float fy = (float)(y * S + sy) + v[sy];
-          __half* dst = tile + lx * cpad + C + (sy * S + sx) * C;
-          for (int k = 0; k < C; ++k) {
-            const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
-            dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+          for (int j = 0; j < SP; ++j) {
+            float fx = (float)X + u[j];
+            float fy = (float)(y * S + s0 + j) + v[j];
+            fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+            fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+            // The four corners are (ya,xa),(ya,xa+1),(ya+1,xa),(ya+1,xa+1) with xa <= W-2, ya <= H-2:
+            // at the far border (fx == W-1) the pair is shifted one to the left and the fraction
+            // becomes 1, which selects the same sample with weight exactly 1 (bit-identical result,
+            // net_utils.py:76 padding_mode='border') -- and the corner addresses are immediates of
+            // two base addresses instead of four independent ones.
+            const int xa = min((int)floorf(fx), W - 2), ya = min((int)floorf(fy), H - 2);
+            ax[j] = fx - (float)xa; ay[j] = fy - (float)ya;
+            o00[j] = ya * W + xa;
+          }
+          float g[SP][3][4];
+          const float* img = hr_prev + (size_t)n * 3 * H * W;
+#pragma unroll
+          for (int j = 0; j < SP; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const float* r0 = img + (size_t)k * H * W + o00[j];
+              const float* r1 = r0 + W;
+              g[j][k][0] = __ldg(r0); g[j][k][1] = __ldg(r0 + 1);
+              g[j][k][2] = __ldg(r1); g[j][k][3] = __ldg(r1 + 1);
+            }
+#pragma unroll
+          for (int j = 0; j < SP; ++j) {
+            // space_to_depth channel (sy*S+sx)*C + k  (net_utils.py:36-47), after the C lr channels
+            __half* dst = tile + lx * tstride + 3 + ((s0 + j) * S + sx) * 3;
+            const float w00 = (1.f - ax[j]) * (1.f - ay[j]), w01 = ax[j] * (1.f - ay[j]);
+            const float w10 = (1.f - ax[j]) * ay[j], w11 = ax[j] * ay[j];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              dst[k] = __float2half(g[j][k][0] * w00 + g[j][k][1] * w01 + g[j][k][2] * w10 + g[j][k][3] * w11);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < SP; ++j) {
+            const float fx = (float)X + u[j];
+            const float fy = (float)(y * S + s0 + j) + v[j];
+            __half* dst = tile + lx * tstride + C + ((s0 + j) * S + sx) * C;
+            for (int k = 0; k < C; ++k) {
+              const float* plane = hr_prev + ((size_t)n * C + k) * H * W;
+              dst[k] = __float2half(bilerp_border(plane, H, W, fx, fy));
+            }
           }
         }
       }
@@ -179,9 +190,11 @@ warp_s2d_concat_kernel(const float* __restrict__ hr_prev, const float* __restric
     // coalesced store of min(LRW, w-x0) pixels * cpad halves (cpad*2 bytes, multiple of 16)
     const int npx = min(LRW, w - x0);
     const int vec_per_px = cpad / 8;  // uint4 per pixel
-    const uint4* src = reinterpret_cast<const uint4*>(tile);
     uint4* dstg = reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0) * cpad);
-    for (int i = t; i < npx * vec_per_px; i += 128) dstg[i] = src[i];
+    for (int i = t; i < npx * vec_per_px; i += 128) {
+      const int px = i / vec_per_px, vv = i - px * vec_per_px;
+      dstg[i] = *reinterpret_cast<const uint4*>(tile + px * tstride + vv * 8);
+    }
     __syncthreads();
   }
 }
@@ -548,13 +561,20 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   const int lrw = 128 / s;
   constexpr int RY = 2;
   dim3 grid(tg_ceil_div(w, lrw), tg_ceil_div(h, RY), n);
-  const size_t smem = (size_t)lrw * cpad * sizeof(__half);
+  const size_t smem = (size_t)lrw * (cpad + 8) * sizeof(__half);   // tile pixel stride = cpad*2 + 16 bytes
   __half* o = (__half*)out;
   TG_REQUIRE(s * h >= 2 && s * w >= 2, TG_E_UNSUPPORTED, "warp_s2d_concat: HR image smaller than 2x2");
   const int fm = !lrflow ? 0 : (up_mode == TG_UP_BICUBIC ? 1 : 2);
-#define TG_WARP_LAUNCH(SS, FM)                                                                              \
-  tg_launch(warp_s2d_concat_kernel<SS, FM, RY>, dim3(grid), dim3(128), smem, st, hr_prev, flow, lr_curr, o, \
-            c, h, w, h8, w8, cpad)
+  // TG_WARP_SP=full: all S HR rows of an LR row per pass (the round-1 kernel shape, A/B measurements)
+  static int sp_full = -1;
+  if (sp_full < 0) { const char* e = getenv("TG_WARP_SP"); sp_full = (e && e[0] == 'f') ? 1 : 0; }
+#define TG_WARP_LAUNCH(SS, FM)                                                                                 \
+  do {                                                                                                         \
+    if (sp_full) tg_launch(warp_s2d_concat_kernel<SS, FM, RY, SS>, dim3(grid), dim3(128), smem, st, hr_prev,    \
+                           flow, lr_curr, o, c, h, w, h8, w8, cpad);                                           \
+    else tg_launch(warp_s2d_concat_kernel<SS, FM, RY, 2>, dim3(grid), dim3(128), smem, st, hr_prev, flow,       \
+                   lr_curr, o, c, h, w, h8, w8, cpad);                                                         \
+  } while (0)
   if (s == 4) {
     if (fm == 0) TG_WARP_LAUNCH(4, 0); else if (fm == 1) TG_WARP_LAUNCH(4, 1); else TG_WARP_LAUNCH(4, 2);
   } else {
@@ -591,11 +611,10 @@ int tg_downsample_bd_nchw_f32(const float* x, const float* k2d, float* y, int n,
   const int oh = (Hp - k) / s + 1, ow = (Wp - k) / s + 1;
   TG_REQUIRE((size_t)n * c <= 65535, TG_E_UNSUPPORTED, "downsample_bd: n*c too large");
   const size_t smem = ((size_t)k * k + (size_t)(7 * s + k) * (31 * s + k)) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(downsample_bd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    attr_done = true;
-  }
+  static TgPerDeviceOnce attr_once;
+  attr_once.run([] {
+    return cudaFuncSetAttribute(downsample_bd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  });
   TG_REQUIRE(smem <= 160 * 1024, TG_E_UNSUPPORTED, "downsample_bd: tile does not fit in shared memory");
   dim3 grid(tg_ceil_div(ow, 32), tg_ceil_div(oh, 8), n * c);
   tg_launch(downsample_bd_kernel, grid, dim3(256), smem, (cudaStream_t)stream, x, k2d, y, H, W, oh, ow, k, s, pad);

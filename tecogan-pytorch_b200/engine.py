@@ -6,7 +6,9 @@ the reference does an H2D copy, ~60 library launches, a device sync, a D2H copy 
 uint8 conversion per frame; here a frame is one graph replay, the uint8/HWC conversion is a
 kernel (tg_float_to_uint8_nhwc) and the copies overlap compute on side streams.
 """
+import collections
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -20,7 +22,9 @@ def _use_graph():
 
 class ClipEngine:
     def __init__(self, net, n, c, h, w, device, use_graph=None):
-        self.net, self.n, self.c, self.h, self.w = net, n, c, h, w
+        # weak reference: the engine cache below must not keep a dropped net (and its graphs) alive
+        self._net = weakref.ref(net)
+        self.n, self.c, self.h, self.w = n, c, h, w
         self.device = torch.device(device)
         s = net.scale
         self.H, self.W = s * h, s * w
@@ -38,6 +42,19 @@ class ClipEngine:
             self.stage = None
             if self.use_graph:
                 self._capture()
+
+    @property
+    def net(self):
+        net = self._net()
+        if net is None:
+            raise ops.L.TecoganB200Error('ClipEngine: the FRNet it was built for has been deleted')
+        return net
+
+    def close(self):
+        """Drop the CUDA graphs (and their private memory pool) and the static buffers."""
+        self.graphs = [None, None]
+        self.lr = self.hr = self.u8 = []
+        self.stage = None
 
     # one frame: parity p consumes lr[p] (current), lr[p^1] (previous), hr[p^1] -> hr[p], u8[p]
     def _enqueue(self, p):
@@ -128,19 +145,53 @@ class ClipEngine:
         return out_host
 
 
-_ENGINES = {}
+# Engines are cached per net (weakly: deleting the net frees its engines) and per clip geometry,
+# least-recently-used first; at most TECOGAN_B200_MAX_ENGINES (default 3) geometries per net stay
+# captured -- each holds two CUDA graphs and their pool (hundreds of MB to a few GB at video sizes).
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def _max_engines():
+    return max(1, int(os.environ.get('TECOGAN_B200_MAX_ENGINES', '3')))
+
+
+def _param_signature(net):
+    p = next(net.parameters())
+    return (str(p.device), p.data_ptr())
 
 
 def get_engine(net, n, c, h, w, device):
-    key = (id(net), n, c, h, w, str(device))
-    eng = _ENGINES.get(key)
+    per_net = _ENGINES.get(net)
+    sig = _param_signature(net)
+    if per_net is None or per_net['sig'] != sig:
+        # first use, or the parameters moved (net.to(other device) / re-materialised): captured graphs
+        # would read freed buffers -> drop every engine of this net
+        if per_net is not None:
+            for eng in per_net['lru'].values():
+                eng.close()
+        per_net = _ENGINES[net] = {'sig': sig, 'lru': collections.OrderedDict()}
+    lru = per_net['lru']
+    key = (n, c, h, w, str(device))
+    eng = lru.get(key)
     if eng is None:
-        eng = ClipEngine(net, n, c, h, w, device)
-        _ENGINES[key] = eng
+        while len(lru) >= _max_engines():
+            lru.popitem(last=False)[1].close()
+        eng = lru[key] = ClipEngine(net, n, c, h, w, device)
     else:
+        lru.move_to_end(key)
         # parameters may have changed since capture: repack in place (graphs read the same buffers)
         net.refresh_packed_weights()
     return eng
+
+
+def release_engines(net=None):
+    """Free the cached engines of `net` (all nets when None)."""
+    nets = [net] if net is not None else list(_ENGINES.keys())
+    for k in nets:
+        per_net = _ENGINES.pop(k, None)
+        if per_net is not None:
+            for eng in per_net['lru'].values():
+                eng.close()
 
 
 def infer_clips(net, lr_data, device):

@@ -9,6 +9,21 @@ from . import lib as L
 from . import ops
 
 
+def needs_grad(*tensors):
+    """True when autograd would have to differentiate through an op fed with these tensors."""
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+def no_autograd(name, *tensors):
+    """Ops without a backward kernel refuse inputs that require grad instead of silently cutting
+    the graph (the reference's callers differentiate through backward_warp / upsample_func / fnet:
+    vsr_model.py:86, vsrgan_model.py:106-108,214-222, tecogan_nets.py:419-420)."""
+    if needs_grad(*tensors):
+        raise NotImplementedError(
+            f'tecogan-b200 {name}: no backward kernel for this op -- an input requires grad under '
+            f'autograd; call it under torch.no_grad() or detach the input explicitly')
+
+
 def _f32(t, name):
     if not t.is_cuda:
         raise L.TecoganB200Error(f'{name} must be a CUDA tensor: tecogan-b200 has no CPU path')
@@ -17,6 +32,7 @@ def _f32(t, name):
 
 def space_to_depth(x, scale):
     """Equivalent to tf.space_to_depth(): out[n,(sy*s+sx)*C+c,oh,ow] = x[n,c,oh*s+sy,ow*s+sx]."""
+    no_autograd('space_to_depth', x)
     return ops.space_to_depth(_f32(x, 'x'), scale)
 
 
@@ -25,6 +41,7 @@ def backward_warp(x, flow, mode='bilinear', padding_mode='border'):
     align_corners=True -- the only combination the reference ever uses."""
     if mode != 'bilinear' or padding_mode != 'border':
         raise ValueError(f'Unsupported warp mode: {mode}/{padding_mode}')
+    no_autograd('backward_warp', x, flow)
     return ops.backward_warp(_f32(x, 'x'), _f32(flow, 'flow'))
 
 
@@ -44,6 +61,7 @@ class BicubicUpsampler(nn.Module):
             raise ValueError('tecogan-b200 BicubicUpsampler is built for a=-0.75')
 
     def forward(self, input):
+        no_autograd('BicubicUpsampler', input)
         return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BICUBIC)
 
 
@@ -55,6 +73,7 @@ class BilinearUpsampler:
         self.scale_factor = scale_factor
 
     def __call__(self, input):
+        no_autograd('bilinear upsample_func', input)
         return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BILINEAR)
 
 

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import lib as L
 from . import ops
-from .net_utils import get_upsampling_func, up_mode_of
+from .net_utils import get_upsampling_func, up_mode_of, no_autograd, needs_grad
 
 _LRELU, _RELU = L.ACT_LRELU02, L.ACT_RELU
 
@@ -54,12 +54,13 @@ class _ConvCache:
             pc.refresh(module.weight, module.bias)
         return pc
 
-    def refresh_all(self):
+    def refresh_all(self, force=False):
         """Re-pack (in place) every layer whose parameters changed -- captured CUDA graphs read
         the same packed buffers, so this is all that is needed after an optimizer step or a
-        load_state_dict."""
+        load_state_dict.  force=True repacks unconditionally (needed after ``param.data`` writes,
+        which do not bump the version counter)."""
         for pc, module in self._layers.values():
-            pc.refresh(module.weight, module.bias)
+            pc.refresh(module.weight, module.bias, force=force)
 
 
 class FNet(nn.Module):
@@ -85,6 +86,7 @@ class FNet(nn.Module):
 
     def forward(self, x1, x2):
         """flow from x1 to x2, NCHW fp32 [n,2,8*(h//8),8*(w//8)]"""
+        no_autograd('FNet.forward', x1, x2, *(self.parameters() if self.training else ()))
         x1, x2 = _cuda_f32(x1, 'x1'), _cuda_f32(x2, 'x2')
         a = ops.pack_pair(x1, x2)                       # cat + NHWC fp16 (c64)
         for name, _, _ in self.ENC:
@@ -140,6 +142,7 @@ class SRNet(nn.Module):
 
     def forward(self, lr_curr, hr_prev_tran):
         """lr_curr nchw, hr_prev_tran n(s*s*c)hw (both fp32) -> hr nchw fp32"""
+        no_autograd('SRNet.forward', lr_curr, hr_prev_tran, *(self.parameters() if self.training else ()))
         lr_curr = _cuda_f32(lr_curr, 'lr_curr')
         x = ops.nchw_to_nhwc(torch.cat([lr_curr, _cuda_f32(hr_prev_tran, 'hr_prev_tran')], dim=1))
         return self.run_nhwc(x, lr_curr)
@@ -241,6 +244,7 @@ class FRNet(BaseSequenceGenerator):
     def step_into(self, lr_curr, lr_prev, hr_prev, out):
         """step() writing hr_curr into `out` (nchw fp32, allocated when None).  Enqueues ~45
         kernels on the current stream and nothing else, so it is CUDA-graph capturable."""
+        no_autograd('FRNet.step', lr_curr, lr_prev, hr_prev, *(self.parameters() if self.training else ()))
         lr_curr, lr_prev = _cuda_f32(lr_curr, 'lr_curr'), _cuda_f32(lr_prev, 'lr_prev')
         hr_prev = _cuda_f32(hr_prev, 'hr_prev')
         with torch.no_grad():
@@ -295,9 +299,9 @@ class FRNet(BaseSequenceGenerator):
             return infer_clips(self, lr_data.unsqueeze(0), device)[0]
         return infer_clips(self, lr_data, device)
 
-    def refresh_packed_weights(self):
-        self.fnet._cache.refresh_all()
-        self.srnet._cache.refresh_all()
+    def refresh_packed_weights(self, force=False):
+        self.fnet._cache.refresh_all(force)
+        self.srnet._cache.refresh_all(force)
 
     # ------------------------------------------------------------------ profile protocol
     def generate_dummy_data(self, lr_size, device):

@@ -69,10 +69,13 @@ class PackedConv:
         self._ver = None
         self.refresh(weight, bias)
 
-    def refresh(self, weight, bias):
-        """(Re)pack when the parameters changed (optimizer step / load_state_dict)."""
+    def refresh(self, weight, bias, force=False):
+        """(Re)pack when the parameters changed (optimizer step / load_state_dict).  Change detection
+        is the tensors' version counters + storage pointers; writes through ``param.data`` do not
+        bump the counter -- call with force=True (FRNet.refresh_packed_weights(force=True)) after such
+        an update."""
         ver = (weight._version, bias._version, weight.data_ptr(), bias.data_ptr())
-        if ver == self._ver:
+        if ver == self._ver and not force:
             return
         lib = L.load()
         w = _req(weight.detach(), torch.float32, 'weight', 4)

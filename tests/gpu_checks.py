@@ -559,6 +559,138 @@ def check_bi2_fullsize(h=268, w=640):
     return out
 
 
+# =============================================================================== benchmark workloads
+def _clip_recurrence_vs_oracle(net, p, host_clips, scale, degradation, tag):
+    """infer_sequence (graph ClipEngine, pinned host clips -> host uint8) against the CPU oracle
+    recurrence run on the same clips: per-frame max LSB / differing fraction (drift over time)."""
+    n, t = host_clips.shape[:2]
+    seq = net.infer_sequence(host_clips, torch.device(DEV))          # [n,t,H,W,c] uint8
+    c, h, w = host_clips.shape[2:]
+    assert seq.shape == (n, t, scale * h, scale * w, c) and seq.dtype == np.uint8
+    lr_prev = torch.zeros(n, c, h, w)
+    hr_prev = torch.zeros(n, c, scale * h, scale * w)
+    out = {'max_lsb': 0, 'frac_diff_per_frame': [], 'max_lsb_per_frame': []}
+    for i in range(t):
+        lr_curr = host_clips[:, i].contiguous()
+        hr_prev = O.frnet_step(p, lr_curr, lr_prev, hr_prev, scale, degradation)
+        lr_prev = lr_curr
+        ref_u8 = np.stack([K.float32_to_uint8(hr_prev[k].numpy()).transpose(1, 2, 0) for k in range(n)])
+        d = np.abs(seq[:, i].astype(np.int32) - ref_u8.astype(np.int32))
+        out['max_lsb_per_frame'].append(int(d.max()))
+        out['frac_diff_per_frame'].append(round(float((d != 0).mean()), 5))
+    out['max_lsb'] = max(out['max_lsb_per_frame'])
+    out['frac_diff'] = float(np.mean(out['frac_diff_per_frame']))
+    # fp16 storage vs the fp32 oracle after 8-bit quantisation: never more than 1 LSB on any frame
+    # of any clip, and only where a value sits next to a rounding boundary
+    assert out['max_lsb'] <= 1 and max(out['frac_diff_per_frame']) <= 0.05, (tag, out)
+    return out
+
+
+def check_bench_workload_parity(n=4, t=10):
+    """EXACTLY the e2e workload of bench.py: 4 lock-stepped clips x 10 frames of 3x134x320 from pinned
+    host memory through FRNet.infer_sequence (CUDA-graph ClipEngine, H2D/D2H rings) -> uint8
+    [n,t,536,1280,3], compared per clip and per frame with the CPU oracle recurrence."""
+    import bench
+    net = T.FRNet(3, 3, 64, 10, 'BD', 4)
+    p = bench.make_params()
+    net.load_state_dict(p, strict=True)
+    net = net.to(DEV).eval()
+    host = bench.synthetic_clips(n, t, seed=100).pin_memory()
+    return _clip_recurrence_vs_oracle(net, p, host, 4, 'BD', 'bench 4xBD')
+
+
+def check_bi2_workload_parity(n=1, t=5, h=268, w=640):
+    """BASELINE config 5 at full size: 2x BI, LR 3x268x640 -> 3x536x1280, a t-frame clip through the
+    same engine path, against the CPU oracle recurrence."""
+    net, p = _net(19, 2, 'BI', 1.0)
+    host = torch.stack([O.make_clip(40 + k, t, 3, h, w) for k in range(n)]).pin_memory()
+    return _clip_recurrence_vs_oracle(net, p, host, 2, 'BI', 'config5 2xBI')
+
+
+def check_reference_callers_integration():
+    """Drop-in through the reference's OWN callers (unmodified, from baseline/_ref): VSRModel built
+    from the reference test YAML with define_generator patched to tecogan_b200's, driven through
+    prepare_inference_data -> infer() (reflect pad_sequence, base_model.py:230-251, vsr_model.py:97-113)
+    and compared with the same VSRModel holding the reference generator on the CPU; then main.profile's
+    FLOP report + step loop (main.py:210-264)."""
+    import copy
+    import logging
+    import yaml
+    import refimport
+    models, main = refimport.import_models()
+    yml = os.path.join(refimport.root_dir(), 'experiments_BD', 'FRVSR', 'FRVSR_VimeoTecoGAN_4xSR_2GPU', 'test.yml')
+    opt = yaml.safe_load(open(yml))
+    opt['model']['generator'].pop('load_path', None)          # no checkpoint offline: seeded weights
+    opt.update({'dist': False, 'is_train': False, 'rank': 0, 'world_size': 1})
+    p = O.make_frnet_params(23, gain=1.5)
+    clip = O.make_clip(11, 9, 3, 18, 28)                       # tchw; 18x28 exercises the reflect flow pad
+    data = {'lr': clip.permute(0, 2, 3, 1).contiguous()}       # thwc float, as the datasets deliver it
+
+    def run(device, define_generator):
+        o = copy.deepcopy(opt)
+        o['device'] = device
+        saved = models.vsr_model.define_generator
+        models.vsr_model.define_generator = define_generator
+        try:
+            m = models.vsr_model.VSRModel(o)
+        finally:
+            models.vsr_model.define_generator = saved
+        m.net_G.load_state_dict(p, strict=True)
+        m.prepare_inference_data(data)
+        return m.infer(), m
+
+    ref_seq, _ = run('cpu', models.vsr_model.define_generator)
+    got_seq, m = run(DEV, T.define_generator)
+    assert isinstance(m.net_G, T.FRNet)
+    assert got_seq.shape == ref_seq.shape == (9, 72, 112, 3) and got_seq.dtype == np.uint8
+    d = np.abs(got_seq.astype(np.int32) - ref_seq.astype(np.int32))
+    out = {'infer_max_lsb': int(d.max()), 'infer_frac_diff': float((d != 0).mean())}
+    assert out['infer_max_lsb'] <= 1 and out['infer_frac_diff'] <= 0.03, out
+
+    # main.profile: the reference's FLOP/param report and its 30-iteration step() timing loop
+    records = []
+
+    class _H(logging.Handler):
+        def emit(self, rec):
+            records.append(rec.getMessage())
+
+    lg = logging.getLogger('base')
+    hnd, lvl = _H(), lg.level
+    lg.addHandler(hnd)
+    lg.setLevel(logging.INFO)
+    saved = models.networks.define_generator
+    models.networks.define_generator = T.define_generator
+    try:
+        o = copy.deepcopy(opt)
+        o['device'] = DEV
+        main.profile(o, '3x134x320', test_speed=True)
+    finally:
+        models.networks.define_generator = saved
+        lg.removeHandler(hnd)
+        lg.setLevel(lvl)
+    msg = '\n'.join(records)
+    assert 'FLOPs (10^9): 10.511' in msg and 'FLOPs (10^9): 83.927' in msg and 'FLOPs (10^9): 94.438' in msg, msg
+    assert 'Parameters (10^6): 2.589' in msg and 'Speed:' in msg, msg
+    out['profile_fps_line'] = [ln for ln in msg.splitlines() if ln.startswith('Speed:')][0]
+    return out
+
+
+def check_autograd_guards():
+    """Ops without a backward kernel must refuse inputs that require grad (no silent detach)."""
+    x = rand(1, 1, 3, 16, 16).to(DEV).requires_grad_(True)
+    f = rand(2, 1, 2, 16, 16).to(DEV)
+    n_raised = 0
+    for fn in (lambda: T.space_to_depth(x, 4),):
+        try:
+            fn()
+        except NotImplementedError:
+            n_raised += 1
+    assert n_raised == 1
+    with torch.no_grad():
+        T.space_to_depth(x, 4)
+    return {'raised': n_raised}
+
+
 CHECKS = {
     'warp_hrflow_s4': lambda: check_warp_hrflow(4),
     'warp_hrflow_s2': lambda: check_warp_hrflow(2, h=9, w=70),
@@ -609,5 +741,9 @@ CHECKS = {
     'ragged_sizes': check_ragged_sizes,
     'bi2_fullsize': check_bi2_fullsize,
     'step_vs_oracle_fullsize': check_step_vs_oracle_fullsize,
+    'bench_workload_parity': check_bench_workload_parity,
+    'bi2_workload_parity': check_bi2_workload_parity,
+    'reference_callers_integration': check_reference_callers_integration,
+    'autograd_guards': check_autograd_guards,
     'step_vs_oracle_fullsize_g15': lambda: check_step_vs_oracle_fullsize(gain=1.5, frames=2),
 }

@@ -39,13 +39,45 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LR = (3, 134, 320)
-SCALE = 4
-CLIPS_PER_GPU = 4
-FLOP_PER_FRAME = 94.438e9            # reference counter, SURVEY.md 8-d (FNet 10.511 + SRNet 83.927)
+# The two inference workloads of BASELINE.json; --workload selects one (default: the headline bd4).
+WORKLOADS = {
+    # configs[1]: TecoGAN 4x BD inference, synthetic 3x134x320, batch=4 lock-stepped clips per B200
+    'bd4': dict(lr=(3, 134, 320), scale=4, degradation='BD', clips_per_gpu=4,
+                flop_per_frame=94.438e9,          # reference counter, SURVEY.md 8-d (FNet 10.511 + SRNet 83.927)
+                warp_bytes_per_frame=22983680,    # SURVEY.md 8-d byte formula, fp32
+                metric='hr_frames_per_sec_4xBD_3x134x320',
+                name='TecoGAN 4x BD inference, synthetic 3x134x320 -> 3x536x1280, batch=4 lock-stepped clips per '
+                     'B200 (BASELINE.json configs[1]); clips shard across GPUs, no collective'),
+    # configs[4]: TecoGAN 2x BI inference, synthetic 3x268x640 LR, 30-frame clips, sequence-sharded over GPUs
+    'bi2': dict(lr=(3, 268, 640), scale=2, degradation='BI', clips_per_gpu=2,
+                flop_per_frame=313.916e9,         # FNet 43.019 + SRNet 270.897
+                warp_bytes_per_frame=26071040,
+                metric='hr_frames_per_sec_2xBI_3x268x640',
+                name='TecoGAN 2x BI inference, synthetic 3x268x640 -> 3x536x1280, 30-frame clips, 2 lock-stepped '
+                     'clips per B200 (BASELINE.json configs[4]); clips round-robin over GPUs (main.py:169), '
+                     'no collective'),
+}
+WL = WORKLOADS['bd4']                # set by main()
+LR, SCALE, CLIPS_PER_GPU = WL['lr'], WL['scale'], WL['clips_per_gpu']
 RES_CONV_FLOP_PER_PX = 2 * 9 * 64 * 64
-WARP_BYTES_PER_FRAME_FP32 = 22983680
-PUBLISHED_FPS_1080TI = 27.0            # resources/benchmark.png (GTX 1080 Ti, batch 1)
+PUBLISHED_FPS_1080TI = 27.0            # resources/benchmark.png (GTX 1080 Ti, batch 1, 4x BD 134x320)
+
+
+WL_KEY = 'bd4'
+
+
+def select_workload(name):
+    global WL, WL_KEY, LR, SCALE, CLIPS_PER_GPU
+    WL_KEY = name
+    WL = WORKLOADS[name]
+    LR, SCALE, CLIPS_PER_GPU = WL['lr'], WL['scale'], WL['clips_per_gpu']
+
+
+def workload_config(world):
+    """`config` of the JSON line -- identical for our arm and the reference arm."""
+    return {'workload': WL['name'], 'clips_per_gpu': CLIPS_PER_GPU, 'frames_per_step': CLIPS_PER_GPU * world,
+            'weights': 'seeded random init (no checkpoint)',
+            'l2': 'inputs larger than L2: ~1.3 GB of activations per step >> 126 MB, no explicit flush'}
 
 
 def peaks():
@@ -104,15 +136,15 @@ class ClockSampler:
 
 
 def make_params():
-    from oracle import frnet_oracle as O
-    return O.make_frnet_params(0, scale=SCALE, degradation='BD', gain=1.0)
+    import synthetic
+    return synthetic.make_frnet_params(0, scale=SCALE, degradation=WL['degradation'], gain=1.0)
 
 
 def synthetic_clips(n, t, seed=0):
-    """n smooth translating clips [n,t,3,134,320] -- synthetic data."""
+    """n smooth translating clips [n,t,c,h,w] of the selected workload -- synthetic data."""
     import torch
-    from oracle import frnet_oracle as O
-    base = O.make_clip(seed, min(t, 12), *LR)            # generate 12 frames, then ping-pong in time
+    import synthetic
+    base = synthetic.make_clip(seed, min(t, 12), *LR)    # generate 12 frames, then ping-pong in time
     idx = [i % (2 * len(base) - 2) for i in range(t)]
     idx = [i if i < len(base) else 2 * len(base) - 2 - i for i in idx]
     one = base[idx]
@@ -120,12 +152,10 @@ def synthetic_clips(n, t, seed=0):
 
 
 # =============================================================================== reference arm
-def cpu_reference_fps(steps, warmup, threads=None):
-    """Reference CPU path, 1 clip-frame per step (a bounded sample of the 4-clip step)."""
+def _host_threads(threads=None):
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use the host cores this
+    process may run on (affinity mask, capped at 64: oversubscribing oneDNN's OpenMP pool stalls)."""
     import torch
-    from oracle import frnet_torchref as R
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use the host cores this
-    # process may run on (affinity mask, capped at 64: oversubscribing oneDNN's OpenMP pool stalls)
     if threads is None and torch.get_num_threads() == 1:
         try:
             threads = min(64, len(os.sched_getaffinity(0)))
@@ -133,87 +163,138 @@ def cpu_reference_fps(steps, warmup, threads=None):
             threads = None
     if threads:
         torch.set_num_threads(threads)
-    p = make_params()
+    return torch.get_num_threads()
+
+
+def reference_net(device):
+    """The UNMODIFIED reference FRNet (baseline/_ref, installed by tools/vendor_reference.py) holding the
+    benchmark's seeded weights; None when the install is absent."""
+    import refimport
+    if not refimport.available():
+        return None
+    FRNet, _, _ = refimport.import_generator()
+    net = FRNet(in_nc=3, out_nc=3, nf=64, nb=10, degradation=WL['degradation'], scale=SCALE)
+    net.load_state_dict(make_params(), strict=True)
+    return net.to(device).eval()
+
+
+def cpu_reference_fps(steps, warmup, n=None):
+    """The reference's own CPU path: FRNet.step on `n` lock-stepped clip-frames per step (default: the
+    workload's clips_per_gpu, i.e. the SAME step as our arm), fp32, all host threads.  Falls back to the
+    operator-for-operator port (oracle/frnet_torchref.py) when baseline/_ref is not installed."""
+    import torch
+    n = CLIPS_PER_GPU if n is None else n
+    cores = _host_threads()
     g = torch.Generator().manual_seed(0)
-    lr_curr = torch.rand(1, *LR, generator=g)
-    lr_prev = torch.rand(1, *LR, generator=g)
-    hr_prev = torch.rand(1, LR[0], SCALE * LR[1], SCALE * LR[2], generator=g)
+    lr_curr = torch.rand(n, *LR, generator=g)
+    lr_prev = torch.rand(n, *LR, generator=g)
+    hr_prev = torch.rand(n, LR[0], SCALE * LR[1], SCALE * LR[2], generator=g)
+    net = reference_net('cpu')
+    if net is not None:
+        kind = 'reference'
+        step = lambda a, b, c: net.step(a, b, c)
+    else:
+        from oracle import frnet_torchref as R
+        p = make_params()
+        kind = 'port'
+        step = lambda a, b, c: R.step(p, a, b, c, SCALE, WL['degradation'])
     with torch.no_grad():
         for _ in range(warmup):
-            R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
+            step(lr_curr, lr_prev, hr_prev)
         t0 = time.perf_counter()
         for _ in range(steps):
-            hr_prev = R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
+            hr_prev = step(lr_curr, lr_prev, hr_prev)
         dt = time.perf_counter() - t0
-    return steps / dt, dt, torch.get_num_threads()
+    return n * steps / dt, dt, cores, kind
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    fps, dt, cores = cpu_reference_fps(args.steps, max(args.warmup, 1))
-    sample = (f'{args.steps} steps x 1 clip-frame 3x134x320 -> 3x536x1280 (1 of the {CLIPS_PER_GPU} '
-              f'lock-stepped clips per step), reference CPU ops via oracle/frnet_torchref.py, fp32')
+    n = CLIPS_PER_GPU
+    fps, dt, cores, kind = cpu_reference_fps(args.steps, max(args.warmup, 1))
+    src = ('unmodified reference FRNet.step from baseline/_ref (codes/models/networks/tecogan_nets.py:227-252)'
+           if kind == 'reference' else 'port oracle/frnet_torchref.py (baseline/_ref not installed)')
+    sample = (f'{args.steps} steps x {n} lock-stepped clip-frames {"x".join(map(str, LR))} -> x{SCALE} '
+              f'(the same step as the GPU arm), {src}, fp32, {cores} host threads')
     line = {
-        'impl': 'reference', 'metric': 'hr_frames_per_sec_4xBD_3x134x320', 'value': fps, 'unit': 'frames/s',
+        'impl': 'reference', 'metric': WL['metric'], 'value': fps, 'unit': 'frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'TecoGAN 4x BD inference, synthetic 3x134x320 -> 3x536x1280, CPU reference path',
-                   'clips_per_step': 1},
-        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': workload_config(args.gpus),
+        'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def run_eager_gpu(args, rank):
-    """Context comparator, NOT part of the contract: the reference's operator sequence
-    (oracle/frnet_torchref.py = the F.conv2d / grid_sample / interpolate calls the reference makes)
-    executed by PyTorch's CUDA library kernels (cuDNN) on the same B200, same 4-clip step, timed with
-    CUDA events.  Answers "what does the stock reference get on this GPU" (BASELINE.md section 5)."""
-    if rank != 0:
-        return
+def eager_gpu_results(steps, warmup):
+    """Context comparator: the UNMODIFIED reference FRNet (baseline/_ref) on the same B200 through
+    PyTorch's CUDA library kernels (cuDNN), same lock-stepped step, CUDA events: fp32, TF32 and fp16
+    autocast.  Answers "what does the stock reference get on this GPU" (no B200 number is published)."""
     import torch
-    from oracle import frnet_torchref as R
-    dev = torch.device('cuda', 0)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    net = reference_net(dev)
+    if net is None:
+        return {'unavailable': 'baseline/_ref not installed'}
     torch.backends.cudnn.benchmark = True                      # codes/main.py:216
     g = torch.Generator().manual_seed(0)
     n = CLIPS_PER_GPU
-    base = [torch.rand(n, *LR, generator=g), torch.rand(n, *LR, generator=g),
-            torch.rand(n, LR[0], SCALE * LR[1], SCALE * LR[2], generator=g)]
+    base = [torch.rand(n, *LR, generator=g).to(dev), torch.rand(n, *LR, generator=g).to(dev),
+            torch.rand(n, LR[0], SCALE * LR[1], SCALE * LR[2], generator=g).to(dev)]
     out = {}
-    for name, dtype, tf32, cl in (('fp32', torch.float32, False, False), ('tf32', torch.float32, True, False),
-                                  ('fp16_channels_last', torch.float16, True, True)):
+    for name, tf32, amp in (('fp32', False, False), ('tf32', True, False), ('fp16_autocast', True, True)):
         torch.backends.cudnn.allow_tf32 = tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32
-        p = {k: v.to(dev, dtype) for k, v in make_params().items()}
-        lr_curr, lr_prev, hr_prev = (t.to(dev, dtype) for t in base)
-        if cl:
-            lr_curr, lr_prev, hr_prev = (t.contiguous(memory_format=torch.channels_last)
-                                         for t in (lr_curr, lr_prev, hr_prev))
-        with torch.no_grad():
-            for _ in range(max(args.warmup, 3)):
-                hr_prev = R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                hr_prev = R.step(p, lr_curr, lr_prev, hr_prev, SCALE, 'BD')
-            e1.record()
-            torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
-        out[name] = {'ms_per_step': ms, 'frames_per_s': n * 1e3 / ms}
-    print(json.dumps({'impl': 'eager-gpu', 'metric': 'hr_frames_per_sec_4xBD_3x134x320', 'unit': 'frames/s',
-                      'clips_per_step': n, 'steps': args.steps, 'device': torch.cuda.get_device_name(0),
-                      'note': 'reference operator sequence on PyTorch CUDA library kernels (cuDNN), no uint8/H2D',
-                      'results': out}), flush=True)
+        lr_curr, lr_prev, hr_prev = base
+        try:
+            with torch.no_grad(), torch.autocast('cuda', dtype=torch.float16, enabled=amp):
+                for _ in range(max(warmup, 3)):
+                    hr_prev = net.step(lr_curr, lr_prev, hr_prev).float()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    hr_prev = net.step(lr_curr, lr_prev, hr_prev).float()
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {'ms_per_step': ms, 'frames_per_s': n * 1e3 / ms}
+        except Exception as exc:                               # a mode the stock code cannot run
+            out[name] = {'error': f'{type(exc).__name__}: {exc}'[:200]}
+    torch.backends.cudnn.allow_tf32 = True
+    return {'clips_per_step': n, 'steps': steps, 'unit': 'frames/s', 'results': out,
+            'note': 'unmodified reference FRNet.step on PyTorch CUDA library kernels (cuDNN), device-resident '
+                    'inputs, no uint8/H2D/D2H; includes the reference\'s own CPU-built warp grid + H2D '
+                    '(net_utils.py:62-64)'}
+
+
+def run_eager_gpu(args, rank):
+    if rank != 0:
+        return
+    import torch
+    torch.cuda.set_device(0)
+    res = eager_gpu_results(args.steps, args.warmup)
+    res.update({'impl': 'eager-gpu', 'metric': WL['metric'], 'device': torch.cuda.get_device_name(0)})
+    print(json.dumps(res), flush=True)
 
 
 # =============================================================================== our arm
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv_chain_kernel launch (ncu --set full), or None
-CHAIN_DRAM_TRAFFIC = 23.582976e6 + 2.131712e6     # the 21 layers' activations stay in the 126 MB L2
-CHAIN_DRAM_TRAFFIC_SRC = 'profiles/ncu_chain_r1u.md'
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, taken from the latest
+    `ncu --set full` capture summarised in profiles/ncu_traffic.json (written by
+    tools/summarize_ncu.py --traffic-json from the .ncu-rep of the CURRENT kernels); None when that
+    kernel has no capture -- never a remembered constant."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        ent = json.load(open(path)).get(kernel_key)
+    except Exception:
+        ent = None
+    if not ent:
+        return None, None
+    return float(ent['dram_bytes_per_launch']), ent.get('src')
+
 
 
 def _time_graph(fn, nbuf, reps, torch):
@@ -247,25 +328,23 @@ def time_kernels(dev, pk):
     n, (c, h, w) = CLIPS_PER_GPU, LR
     out = {}
     reps = 60
-    # ---- dominant kernel: SRNet residual-block conv 64->64 (+bias, ReLU), n=4 frames per launch
+    mb = n * h * w * 128 / 1e6                    # one 64-channel fp16 activation map of a step, MB
+    # ---- dominant kernel: SRNet residual-block conv 64->64 (+bias, ReLU), n frames per launch
     wt = torch.randn(64, 64, 3, 3, device=dev) * 0.04
     pc = ops.PackedConv(wt, torch.zeros(64, device=dev), L.CONV_3X3, L.ACT_RELU)
-    nbuf = 10                                   # 10 x (22 MB in + 22 MB out) = 440 MB > 126 MB L2
+    nbuf = max(3, int(220 / mb) + 1)            # bd4: 10 x (22 MB in + 22 MB out) = 440 MB > 126 MB L2
     xs = [torch.randn(n, h, w, 64, device=dev).half() for _ in range(nbuf)]
     ys = [torch.empty_like(x) for x in xs]
     t_conv = _time_graph(lambda i: pc(xs[i], y=ys[i]), nbuf, reps, torch)
     flops = RES_CONV_FLOP_PER_PX * n * h * w
     out['roofline'] = {
-        'kernel': 'conv_tcgen05_kernel<conv3x3, halo> (SRNet resblock conv 64->64, 4 frames/launch)',
+        'kernel': f'conv_tcgen05_kernel<conv3x3, halo> (SRNet resblock conv 64->64, {n} frames/launch)',
         'bound': 'tensor', 'achieved': flops / t_conv / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
         'frac': flops / t_conv / 1e12 / pk['tflops_burst'],
-        # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
-        # (profiles/ncu_conv_r1q.md, launch 1): 22.09 MB read (the fp16 input once) + 0.006 MB
-        # written inside the measured window (the 22 MB output stays in the 126 MB L2)
-        'traffic': 22.09152e6 + 0.006144e6, 'traffic_src': 'profiles/ncu_conv_r1q.md',
+        'traffic': ncu_traffic('conv_single_' + WL_KEY)[0], 'traffic_src': ncu_traffic('conv_single_' + WL_KEY)[1],
         'us_per_launch': t_conv * 1e6, 'flop_per_launch': flops,
         'peak_src': pk['src'] + ' burst (kernel timed alone)',
-        'how': f'{reps} launches in one CUDA graph, {nbuf} rotating in/out pairs (440 MB > L2), CUDA events'}
+        'how': f'{reps} launches in one CUDA graph, {nbuf} rotating in/out pairs ({2 * nbuf * mb:.0f} MB > L2), CUDA events'}
     out['roofline_conv_single'] = out['roofline']
     # ---- dominant kernel of the step: conv_in + 10 residual blocks as ONE persistent launch
     if ops.chain_enabled():
@@ -276,44 +355,44 @@ def time_kernels(dev, pk):
         for b in range(10):
             specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
         chain = ops.ConvChain(specs)
-        nb3 = 3                                  # 3 x (22 MB in + 2 x 22 MB work) = 198 MB > 126 MB L2
+        nb3 = min(3, nbuf)                       # bd4: 3 x (22 MB in + 2 x 22 MB work) = 198 MB > 126 MB L2
         sets = [[xs[i], ys[i], torch.empty_like(xs[i])] for i in range(nb3)]
         creps = 12
         t_chain = _time_graph(lambda i: chain(sets[i]), nb3, creps, torch)
         cflops = flops * nl
         out['roofline'] = {
             'kernel': 'conv_chain_kernel (SRNet conv_in + 10 residual blocks = 21 convs 64->64 in one persistent '
-                      'launch, 4 frames/launch)',
+                      f'launch, {n} frames/launch)',
             'bound': 'tensor', 'achieved': cflops / t_chain / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
             'frac': cflops / t_chain / 1e12 / pk['tflops_burst'],
-            'traffic': CHAIN_DRAM_TRAFFIC, 'traffic_src': CHAIN_DRAM_TRAFFIC_SRC,
+            'traffic': ncu_traffic('conv_chain_' + WL_KEY)[0], 'traffic_src': ncu_traffic('conv_chain_' + WL_KEY)[1],
             'us_per_launch': t_chain * 1e6, 'us_per_layer': t_chain * 1e6 / nl, 'flop_per_launch': cflops,
             'peak_src': pk['src'] + ' burst (kernel timed alone)',
-            'how': f'{creps} launches in one CUDA graph, {nb3} rotating buffer sets (198 MB > L2), CUDA events'}
+            'how': f'{creps} launches in one CUDA graph, {nb3} rotating buffer sets ({3 * nb3 * mb:.0f} MB > L2), CUDA events'}
         del sets
     del xs, ys
     # ---- fused warp + space_to_depth + concat, HR flow given (BASELINE.md byte formula)
     H, W = SCALE * h, SCALE * w
-    nb2 = 6                                      # 6 x 4 frames x ~20 MB = 470 MB > L2
+    nb2 = 6                                      # bd4: 6 x 4 frames x ~20 MB = 470 MB > L2
     hp = [torch.rand(n, c, H, W, device=dev) for _ in range(nb2)]
     fl = [(torch.rand(n, 2, H, W, device=dev) - 0.5) * 6 for _ in range(nb2)]
     lr = [torch.rand(n, c, h, w, device=dev) for _ in range(nb2)]
     oo = [torch.empty(n, h, w, 64, dtype=torch.float16, device=dev) for _ in range(nb2)]
     lf = [(torch.rand(n, 2, h // 8 * 8, w // 8 * 8, device=dev) - 0.5) * 2 for _ in range(nb2)]
+    up_mode = L.UP_BICUBIC if WL['degradation'] == 'BD' else L.UP_BILINEAR
     for variant in ('hrflow', 'lrflow'):
         if variant == 'hrflow':
             call = lambda i: ops.warp_s2d_concat_hrflow(hp[i], fl[i], lr[i], SCALE, out=oo[i])
         else:
-            call = lambda i: ops.warp_s2d_concat_lrflow(hp[i], lf[i], lr[i], SCALE, L.UP_BICUBIC, out=oo[i])
+            call = lambda i: ops.warp_s2d_concat_lrflow(hp[i], lf[i], lr[i], SCALE, up_mode, out=oo[i])
         t = _time_graph(call, nb2, reps, torch)
-        alg = WARP_BYTES_PER_FRAME_FP32 * n
+        alg = WL['warp_bytes_per_frame'] * n
         moved = n * (c * H * W * 4 + (2 * H * W * 4 if variant == 'hrflow' else 2 * (h // 8 * 8) * (w // 8 * 8) * 4)
                      + c * h * w * 4 + h * w * 64 * 2)
         out['roofline_warp' if variant == 'hrflow' else 'roofline_warp_fused_lrflow'] = {
-            'kernel': f'warp_s2d_concat_kernel<4,{variant}> (4 frames/launch)', 'bound': 'hbm',
+            'kernel': f'warp_s2d_concat_kernel<{SCALE},{variant}> ({n} frames/launch)', 'bound': 'hbm',
             'achieved': alg / t / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': alg / t / 1e9 / pk['hbm_gbs'],
-            # one `ncu --set full` capture of the LR-flow variant (profiles/ncu_warp_r1x.md)
-            'traffic': (36.009728e6 + 0.312576e6) if variant == 'lrflow' else None,
+            'traffic': ncu_traffic(f'warp_{variant}_' + WL_KEY)[0], 'traffic_src': ncu_traffic(f'warp_{variant}_' + WL_KEY)[1],
             'us_per_launch': t * 1e6, 'algorithmic_bytes_per_launch': alg,
             'bytes_actually_moved_per_launch': moved, 'moved_gbs': moved / t / 1e9,
             'peak_src': pk['src'], 'how': f'{reps} launches in one CUDA graph, {nb2} rotating buffer sets > L2'}
@@ -334,7 +413,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=dev)
     pk = peaks()
 
-    net = T.FRNet(3, 3, 64, 10, 'BD', SCALE)
+    net = T.FRNet(3, 3, 64, 10, WL['degradation'], SCALE)
     net.load_state_dict(make_params(), strict=True)
     net = net.to(dev).eval()
     n, (c, h, w) = CLIPS_PER_GPU, LR
@@ -382,8 +461,34 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             sampler.stop()
         return
+    # ---------------- sustained: >= args.sustain_s seconds of back-to-back steps (clocks settle under load)
+    sustained = None
+    if args.sustain_s > 0:
+        n_sus = max(K, int(args.sustain_s / (ms_max / K * 1e-3)) + 1)
+        sus_sampler = ClockSampler(local_rank)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            sus_sampler.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for i in range(n_sus):
+            step(i)
+        s1.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            sus_ms = float(ts.item())
+            sustained = {'value': world * n * n_sus / (sus_ms * 1e-3), 'unit': 'frames/s', 'steps': n_sus,
+                         'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / n_sus, 'clocks': sus_sampler.stop(),
+                         'model_tflops': world * n * n_sus / (sus_ms * 1e-3) * WL['flop_per_frame'] / 1e12 / world,
+                         'how': 'same device-resident step loop as `value`, run for >= %.0f s' % args.sustain_s}
+
     # ---------------- end to end through FRNet.infer_sequence with host buffers
-    t_e2e = max(K, 4)
+    t_e2e = max(K, 4) if WL_KEY == 'bd4' else 30           # config 5 is quoted on 30-frame clips
     host_clips = synthetic_clips(n, t_e2e, seed=100 + rank).pin_memory()     # [n,T,c,h,w] pinned
     net.infer_sequence(host_clips[:, :4], dev)                                # warm-up
     net.infer_sequence(host_clips, dev)
@@ -403,29 +508,34 @@ def run_ours(args, rank, world, local_rank):
 
     line = None
     if rank == 0:
+        del eng, clips, frames
+        T.engine.release_engines(net)
+        torch.cuda.empty_cache()
         roof = time_kernels(dev, pk)
-        cpu = None
+        cpu, eager = None, None
         if world == 1:
-            steps_cpu = 24
-            fps, dt, cores = cpu_reference_fps(steps_cpu, 2)
-            cpu = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-                   'sample': f'{steps_cpu} clip-frames 3x134x320 -> 3x536x1280 (fp32, PyTorch CPU library ops as the '
-                             f'reference uses, oracle/frnet_torchref.py), {dt:.1f} s of CPU work'}
+            steps_cpu = 6 if WL_KEY == 'bd4' else 3
+            fps, dt, cores, kind = cpu_reference_fps(steps_cpu, 1)
+            cpu = {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                   'sample': f'{steps_cpu} steps x {n} lock-stepped clip-frames {"x".join(map(str, LR))} (fp32, '
+                             + ('unmodified reference FRNet.step from baseline/_ref' if kind == 'reference' else
+                                'port oracle/frnet_torchref.py') + f'), {dt:.1f} s of CPU work'}
+            if not args.no_eager:
+                eager = eager_gpu_results(10, 3)
         line = {
-            'metric': 'hr_frames_per_sec_4xBD_3x134x320', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+            'metric': WL['metric'], 'value': value, 'unit': 'frames/s', 'n_gpus': world,
             'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': value / PUBLISHED_FPS_1080TI, 'dtype': 'f16', 'data': 'synthetic',
-            'config': {
-                'workload': 'TecoGAN 4x BD inference, synthetic 3x134x320 -> 3x536x1280, batch=4 lock-stepped '
-                            'clips per B200 (BASELINE.json configs[1]); clips shard across GPUs, no collective',
-                'clips_per_gpu': n, 'frames_per_step': n * world, 'weights': 'seeded random init (no checkpoint)',
-                'l2': 'per-step working set ~1.3 GB of activations (conv_up output alone 351 MB) >> 126 MB L2; '
-                      'no explicit flush', 'conv_impl': ops.default_conv_impl(),
-                'baseline_note': 'vs_baseline = value / 27 FPS published for 1x GTX 1080 Ti, batch 1 '
+            'vs_baseline': (value / PUBLISHED_FPS_1080TI) if WL_KEY == 'bd4' else None, 'dtype': 'f16',
+            'data': 'synthetic',
+            'config': workload_config(world),
+            'notes': {
+                'l2': 'per-step working set ~1.3 GB of activations (HR 64-channel map alone 351 MB for 4 frames) '
+                      '>> 126 MB L2; no explicit flush', 'conv_impl': ops.default_conv_impl(),
+                'baseline_note': 'vs_baseline = value / 27 FPS published for 1x GTX 1080 Ti, batch 1, 4x BD '
                                  '(resources/benchmark.png); no B200 number is published'},
-            'gflop_per_frame': FLOP_PER_FRAME / 1e9,
-            'model_tflops': value * FLOP_PER_FRAME / 1e12 / world,
-            'model_tensor_frac_of_sustained': value * FLOP_PER_FRAME / 1e12 / world / pk['tflops_sustained'],
+            'gflop_per_frame': WL['flop_per_frame'] / 1e9,
+            'model_tflops': value * WL['flop_per_frame'] / 1e12 / world,
+            'model_tensor_frac_of_sustained': value * WL['flop_per_frame'] / 1e12 / world / pk['tflops_sustained'],
             'e2e': {'value': e2e_val, 'unit': 'frames/s', 'h2d_bytes_per_step': n * c * h * w * 4,
                     'd2h_bytes_per_step': n * SCALE * h * SCALE * w * c, 'steps': t_e2e,
                     'api': 'FRNet.infer_sequence(lr_data[n,t,c,h,w] pinned host) -> uint8 ndarray [n,t,H,W,c]'},
@@ -433,8 +543,12 @@ def run_ours(args, rank, world, local_rank):
             'clocks': clocks,
         }
         line.update(roof)
+        if sustained is not None:
+            line['sustained'] = sustained
         if cpu is not None:
             line['cpu_baseline'] = cpu
+        if eager is not None:
+            line['gpu_eager_baseline'] = eager
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -448,9 +562,14 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'eager-gpu'])
+    ap.add_argument('--workload', default='bd4', choices=sorted(WORKLOADS),
+                    help='bd4 = BASELINE configs[1] (headline); bi2 = configs[4] (2x BI 268x640, 30-frame clips)')
+    ap.add_argument('--sustain-s', type=float, default=3.0, help='seconds of the sustained block (0 = skip)')
+    ap.add_argument('--no-eager', action='store_true', help='skip the gpu_eager_baseline block (N=1 only)')
     ap.add_argument('--profile-only', action='store_true',
                     help='run only the device-resident step loop (for ncu captures); prints nothing')
     args = ap.parse_args()
+    select_workload(args.workload)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))

@@ -19,18 +19,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-REF = '/root/reference/codes'
 
 
 def import_reference():
-    sys.path.insert(0, REF)
-    m = types.ModuleType('metrics')
-    m.__path__ = [REF + '/metrics']          # skip metrics/__init__ (LPIPS -> skimage/IPython)
-    sys.modules['metrics'] = m
-    sys.modules.setdefault('lmdb', types.ModuleType('lmdb'))
-    from models.networks.tecogan_nets import FRNet          # noqa: E402
-    from utils import net_utils, data_utils                 # noqa: E402
-    return FRNet, net_utils, data_utils
+    import refimport                                        # SURVEY.md section 9 recipe, no reference edits
+    return refimport.import_generator()
 
 
 def rand(seed, *shape, lo=0.0, hi=1.0):

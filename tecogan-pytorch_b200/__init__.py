@@ -8,7 +8,8 @@ from .net_utils import (space_to_depth, backward_warp, get_upsampling_func,  # n
                         BicubicUpsampler, BilinearUpsampler)
 from .data_utils import create_kernel, downsample_bd  # noqa: F401
 from .factory import define_generator  # noqa: F401
-from .engine import infer_clips, ClipEngine  # noqa: F401
+from . import engine  # noqa: F401
+from .engine import infer_clips, ClipEngine, release_engines  # noqa: F401
 from .sharding import clips_for_rank  # noqa: F401
 
 __all__ = ['FRNet', 'FNet', 'SRNet', 'define_generator', 'space_to_depth', 'backward_warp',

@@ -86,8 +86,9 @@ class FNet(nn.Module):
 
     def forward(self, x1, x2):
         """flow from x1 to x2, NCHW fp32 [n,2,8*(h//8),8*(w//8)]"""
-        no_autograd('FNet.forward', x1, x2, *(self.parameters() if self.training else ()))
+        g1, g2 = x1, x2
         x1, x2 = _cuda_f32(x1, 'x1'), _cuda_f32(x2, 'x2')
+        no_autograd('FNet.forward', g1, g2, *(self.parameters() if self.training else ()))
         a = ops.pack_pair(x1, x2)                       # cat + NHWC fp16 (c64)
         for name, _, _ in self.ENC:
             a = self._conv(name, 0, _LRELU)(a)
@@ -142,8 +143,9 @@ class SRNet(nn.Module):
 
     def forward(self, lr_curr, hr_prev_tran):
         """lr_curr nchw, hr_prev_tran n(s*s*c)hw (both fp32) -> hr nchw fp32"""
-        no_autograd('SRNet.forward', lr_curr, hr_prev_tran, *(self.parameters() if self.training else ()))
+        g1 = lr_curr
         lr_curr = _cuda_f32(lr_curr, 'lr_curr')
+        no_autograd('SRNet.forward', g1, hr_prev_tran, *(self.parameters() if self.training else ()))
         x = ops.nchw_to_nhwc(torch.cat([lr_curr, _cuda_f32(hr_prev_tran, 'hr_prev_tran')], dim=1))
         return self.run_nhwc(x, lr_curr)
 
@@ -244,9 +246,10 @@ class FRNet(BaseSequenceGenerator):
     def step_into(self, lr_curr, lr_prev, hr_prev, out):
         """step() writing hr_curr into `out` (nchw fp32, allocated when None).  Enqueues ~45
         kernels on the current stream and nothing else, so it is CUDA-graph capturable."""
-        no_autograd('FRNet.step', lr_curr, lr_prev, hr_prev, *(self.parameters() if self.training else ()))
+        g = (lr_curr, lr_prev, hr_prev)
         lr_curr, lr_prev = _cuda_f32(lr_curr, 'lr_curr'), _cuda_f32(lr_prev, 'lr_prev')
         hr_prev = _cuda_f32(hr_prev, 'hr_prev')
+        no_autograd('FRNet.step', *g, *(self.parameters() if self.training else ()))
         with torch.no_grad():
             lr_flow = self.fnet(lr_curr, lr_prev)
             # reflect-pad + upsample_func + *scale + warp + space_to_depth + concat: one kernel

@@ -201,7 +201,9 @@ def test_bench_reference_arm_contract():
               'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
         assert k in d, k
     assert d['impl'] == 'reference' and d['value'] > 0 and d['higher_is_better'] is True
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    import refimport
+    assert d['cpu_baseline']['kind'] == ('reference' if refimport.available() else 'port') and d['cpu_baseline']['cores'] >= 1
+    assert d['config']['clips_per_gpu'] == 4          # the same 4-clip step as the GPU arm
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     # a non-zero rank exits 0 without work or output
     env.update(RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')

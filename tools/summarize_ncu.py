@@ -3,7 +3,12 @@
 discussion needs, plus the top stall sites of the source page.
 
     python tools/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/ncu_<kernel>_rNN.md
+    python tools/summarize_ncu.py gpurun_out/prof.ncu-rep --traffic-key conv_chain_bd4 [--launch K]
+        additionally records dram read+write bytes of launch K (default: the longest launch) under that
+        key in profiles/ncu_traffic.json -- the file bench.py reads `roofline.traffic` from.
 """
+import json
+import os
 import csv
 import io
 import subprocess
@@ -27,9 +32,31 @@ def run(args):
     return subprocess.run(['ncu'] + args, capture_output=True, text=True).stdout
 
 
-def main(rep):
+def _bytes(val, unit):
+    v = float(val.replace(',', ''))
+    return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
+
+
+def record_traffic(rep, hdr, units, rows, key, launch):
+    ird, iwr, it = hdr.index('dram__bytes_read.sum'), hdr.index('dram__bytes_write.sum'), hdr.index('gpu__time_duration.sum')
+    if launch is None:
+        launch = max(range(len(rows)), key=lambda k: float(rows[k][it].replace(',', '')))
+    r = rows[launch]
+    ent = {'dram_bytes_per_launch': _bytes(r[ird], units[ird]) + _bytes(r[iwr], units[iwr]),
+           'dram_read_bytes': _bytes(r[ird], units[ird]), 'dram_write_bytes': _bytes(r[iwr], units[iwr]),
+           'kernel': r[hdr.index('Kernel Name')][:80], 'launch': launch,
+           'src': f'ncu --set full capture {os.path.basename(rep)} (see profiles/)'}
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'ncu_traffic.json')
+    data = json.load(open(path)) if os.path.isfile(path) else {}
+    data[key] = ent
+    json.dump(data, open(path, 'w'), indent=1, sort_keys=True)
+
+
+def main(rep, traffic_key=None, launch=None):
     raw = list(csv.reader(io.StringIO(run(['-i', rep, '--page', 'raw', '--csv']))))
     hdr, units, rows = raw[0], raw[1], raw[2:]
+    if traffic_key:
+        record_traffic(rep, hdr, units, rows, traffic_key, launch)
     print(f'# ncu --set full summary: {rep}\n')
     name_i = hdr.index('Kernel Name')
     for k, r in enumerate(rows):
@@ -78,4 +105,7 @@ def main(rep):
 
 
 if __name__ == '__main__':
-    main(sys.argv[1])
+    a = sys.argv[1:]
+    key = a[a.index('--traffic-key') + 1] if '--traffic-key' in a else None
+    lk = int(a[a.index('--launch') + 1]) if '--launch' in a else None
+    main(a[0], key, lk)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 1
+#define TG_ABI_VERSION 2   /* 2: tg_conv_desc.mask, backward (training) entry points */
 #define TG_TAPN_ROWS 48   /* 9 taps x 4 output channels, padded to a multiple of 16 */
 
 enum {
@@ -40,8 +40,19 @@ enum {
   TG_E_DRIVER = -3        /* cuTensorMapEncodeTiled unavailable or failed    */
 };
 
-enum { TG_ACT_NONE = 0, TG_ACT_RELU = 1, TG_ACT_LRELU02 = 2 };
-enum { TG_CONV_3X3 = 0, TG_CONVT_3X3_S2 = 1 };
+enum {
+  TG_ACT_NONE = 0, TG_ACT_RELU = 1, TG_ACT_LRELU02 = 2,
+  /* data-gradient epilogues: y = (conv + bias [+ residual]) * act'(mask), the derivative taken from
+   * the STORED forward output `mask` of the layer the gradient flows into (sign(out) == sign(pre-act)) */
+  TG_ACT_DRELU = 3,     /* * (mask > 0 ? 1 : 0)   */
+  TG_ACT_DLRELU02 = 4   /* * (mask > 0 ? 1 : 0.2) */
+};
+enum {
+  TG_CONV_3X3 = 0,
+  TG_CONVT_3X3_S2 = 1,
+  TG_CONV_3X3_S2 = 2    /* stride-2 conv, pad 1: y[oy,ox] = sum x[2oy+ky-1, 2ox+kx-1] * w[.,.,ky,kx] -- the data
+                           gradient of TG_CONVT_3X3_S2 (tcgen05: tap mode over the four parity planes of x) */
+};
 enum { TG_UP_BICUBIC = 0, TG_UP_BILINEAR = 1 };
 enum {
   TG_EPI_NHWC_F16 = 0,      /* y = act(conv + bias) [+ residual]  -> NHWC fp16        */
@@ -69,6 +80,16 @@ int tg_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, void* packed
  * (tecogan_nets.py:119-126) -> 9 tiles grouped by output parity (1/2/2/4 taps) */
 int tg_pack_convT3x3s2_weights(const float* w_iohw, int cin, int cout, void* packed,
                                int cout_pad, int cin_pad, void* stream);
+/* Data-gradient operands (autograd of the above under loss.backward(), vsr_model.py:92):
+ *  - conv3x3 dgrad = conv3x3 of dz with the taps flipped and cin/cout swapped: packs
+ *    w'[ci][co][ky][kx] = w[co][ci][2-ky][2-kx] from the nn.Conv2d weight [cout,cin,3,3]; run it as a
+ *    TG_CONV_3X3 layer with cin_pad(layer) = pad(cout), cout_pad(layer) = pad(cin).
+ *  - convT dgrad = TG_CONV_3X3_S2 over dz with w'[ci][co][ky][kx] = wt[ci][co][ky][kx]: the
+ *    nn.ConvTranspose2d weight [cin,cout,3,3] read as an OIHW conv weight (out = cin, in = cout). */
+int tg_pack_conv3x3_weights_dgrad(const float* w_oihw, int cout, int cin, void* packed, int cin_as_cout_pad,
+                                  int cout_as_cin_pad, void* stream);
+int tg_pack_conv3x3s2_weights(const float* w_oihw, int cout, int cin, void* packed, int cout_pad, int cin_pad,
+                              void* stream);
 /* Thin heads (cout <= 4: FNet flow head 32->2, SRNet conv_out 64->3) use the "tap-major N"
  * layout: one tile per 64-ch chunk, [48 rows][64 k], row = tap*4 + co (rows >= 36 zero).  One
  * MMA group then yields all nine tap products of a pixel (N = 48) and the 3x3 shift-add happens
@@ -86,12 +107,13 @@ int tg_pack_conv3x3_weights_tapn(const float* w_oihw, int cout, int cin, void* p
  * store: a read-modify-write there exposes a global-load round trip per tile).
  * ---------------------------------------------------------------------- */
 typedef struct tg_conv_desc {
-  const void* x;        /* NHWC fp16 [n,h,w,cin]                                         */
+  const void* x;        /* NHWC fp16 [n,h,w,cin]  (TG_CONV_3X3_S2: [n,2h,2w,cin])                */
   const void* weights;  /* packed weights (tg_pack_*)                                    */
   const float* bias;    /* fp32 [cout] (zero padded)                                     */
   const void* residual; /* NHWC fp16 [n,h,w,cout] or NULL (TG_EPI_NHWC_F16, conv3x3 only) */
   void* y;              /* see epilogue; convT writes [n,2h,2w,cout]                     */
-  int32_t n, h, w;      /* input batch / height / width                                  */
+  int32_t n, h, w;      /* batch and the height / width the kernel tiles over: the input's (= the
+                           output's for conv3x3; convT writes 2h x 2w), the OUTPUT's for TG_CONV_3X3_S2 */
   int32_t cin, cout;    /* stored channel counts: cin in {64,128,256}; cout in {64,128,256}
                            for TG_EPI_NHWC_F16, 48 (= TG_TAPN_ROWS, tap-major N packing)
                            for the two NCHW epilogues                                    */
@@ -102,6 +124,7 @@ typedef struct tg_conv_desc {
   int32_t a_mode;       /* TG_AMODE_* (tcgen05 kernel only; AUTO = fastest validated)    */
   int32_t max_ctas;     /* 0 = one persistent CTA per SM                                 */
   int32_t reserved;     /* must be 0                                                     */
+  const void* mask;     /* TG_ACT_DRELU / TG_ACT_DLRELU02: NHWC fp16, shape of y; else NULL */
 } tg_conv_desc;
 
 int tg_conv_tcgen05(const tg_conv_desc* d, void* stream);
@@ -197,6 +220,78 @@ int tg_float_to_uint8_nhwc(const float* x, uint8_t* y, int n, int c, int h, int 
  * x NCHW fp32 [n,c,H,W] -> y [n,c,h,w] with h = (Hp-k)/s+1, Hp = H (+k-1 when pad_data). */
 int tg_downsample_bd_nchw_f32(const float* x, const float* k2d, float* y, int n, int c, int H, int W,
                               int k, int s, int pad_data, void* stream);
+
+/* ========================================================================
+ * Training: the generator backward.  Replaces autograd through
+ * FRNet.forward_sequence (tecogan_nets.py:174-225) under loss_G.backward() (vsr_model.py:92,
+ * vsrgan_model.py:273) and through backward_warp / upsample_func / fnet at the module boundary
+ * (vsr_model.py:86, vsrgan_model.py:106-108,214-222, tecogan_nets.py:419-453).
+ *
+ * fp16 gradients between conv layers carry a power-of-two LOSS SCALE held in device memory:
+ * `scale` points at two floats {scale, 1/scale} (tg_grad_scale_from_amax / tg_flow_head_bwd write
+ * them); kernels producing fp32 results multiply by 1/scale.  scale == NULL means 1.
+ * ====================================================================== */
+size_t tg_grad_scale_workspace_bytes(void);   /* 16: {scale, 1/scale} fp32 + amax scratch (zero it once) */
+/* scale = 2^floor(log2(target / max(|a|,|b|))) clamped to 2^+-24 (1 when all-zero); b may be NULL */
+int tg_grad_scale_from_amax(const float* a, size_t na, const float* b, size_t nb, float target, void* ws,
+                            void* stream);
+/* (a [+ b]) * scale : NCHW fp32 [n,c,h,w] -> NHWC fp16 [n,h,w,cpad] (pad channels zero) */
+int tg_grad_pack_nhwc_f16(const float* a, const float* b, const float* scale, void* y, int n, int c, int h, int w,
+                          int cpad, void* stream);
+/* channels [c_offset, c_offset+c) of NHWC fp16 -> NCHW fp32 * 1/scale ; accumulate != 0 adds into y */
+int tg_grad_unpack_nchw_f32(const void* x, const float* scale, float* y, int n, int c, int h, int w, int cpad,
+                            int c_offset, int accumulate, void* stream);
+/* db[ch] += 1/scale * sum_pixels dz[p][ch], ch < c_real  (bias gradient of any conv layer) */
+int tg_bias_grad_nhwc_f16(const void* dz, size_t npix, int c, int c_real, const float* scale, float* db,
+                          void* stream);
+
+/* Weight gradient of a conv3x3 / convT3x3s2 layer: dw += 1/scale * sum_p x[p+tap] (x) dz[p], written in
+ * the parameter's own layout (nn.Conv2d [cout_real,cin_real,3,3]; nn.ConvTranspose2d
+ * [cin_real,cout_real,3,3]) with fp32 atomics -- the caller zeroes dw (or accumulates on purpose).
+ * tcgen05: GEMM over pixels (K), x and dz both channel-contiguous ("MN-major") operands. */
+typedef struct tg_wgrad_desc {
+  const void* x;        /* layer input,  NHWC fp16 [n,h,w,cin]                              */
+  const void* dz;       /* gradient of the pre-activation output, NHWC fp16 [n,h,w,cout]
+                           (convT: [n,2h,2w,cout]), loss-scaled                           */
+  float* dw;            /* fp32 gradient, parameter layout                                  */
+  const float* scale;   /* {scale, 1/scale} or NULL                                         */
+  int32_t n, h, w;      /* of the layer INPUT                                               */
+  int32_t cin, cout;    /* stored channel counts (64/128/256)                               */
+  int32_t cin_real, cout_real;
+  int32_t kind;         /* TG_CONV_3X3 | TG_CONVT_3X3_S2                                    */
+  int32_t max_ctas;     /* 0 = all SMs                                                      */
+  int32_t reserved;     /* must be 0                                                        */
+} tg_wgrad_desc;
+int tg_wgrad_tcgen05(const tg_wgrad_desc* d, void* stream);
+int tg_wgrad_simt(const tg_wgrad_desc* d, void* stream);    /* CUDA-core cross-check (tests only) */
+
+/* grid_sample(bilinear, border, align_corners) backward = autograd of net_utils.backward_warp
+ * (net_utils.py:50-82): gx += scatter(gy) (fp32 atomics, caller zeroes gx), gflow = gather; either
+ * output may be NULL. */
+int tg_backward_warp_bwd_nchw_f32(const float* x, const float* flow, const float* gy, float* gx, float* gflow,
+                                  int n, int c, int h, int w, void* stream);
+/* gradient of tg_warp_s2d_concat_hrflow w.r.t. hr_prev (atomic accumulate) and hr_flow (store), from the
+ * loss-scaled NHWC fp16 gradient `gx` of the SRNet input; either output may be NULL */
+int tg_warp_s2d_concat_bwd(const void* gx, const float* hr_prev, const float* hr_flow, const float* scale,
+                           float* d_hr_prev, float* d_hr_flow, int n, int c, int h, int w, int s, int cpad,
+                           void* stream);
+/* gradient of y = mul * upsample_func(x): gy [n,c,s*h,s*w] -> gx [n,c,h,w] (net_utils.py:85-156) */
+int tg_upsample_bwd_nchw_f32(const float* gy, float* gx, int n, int c, int h, int w, int s, int up_mode, float mul,
+                             int accumulate, void* stream);
+/* FNet helpers (tecogan_nets.py:28,35,42,74-79), each fused with the activation derivative of the conv
+ * layer whose stored output is `x` / `m` (act = that layer's TG_ACT_*):
+ *   maxpool:  gx[n,h,w,c] = route(gy[n,h/2,w/2,c]) * act'(x)      upsample2x: gx[n,h,w,c] = T(gy[n,2h,2w,c]) * act'(m) */
+int tg_maxpool2x2_bwd_nhwc_f16(const void* x, const void* gy, void* gx, int n, int h, int w, int c, int act,
+                               void* stream);
+int tg_upsample2x_bilinear_bwd_nhwc_f16(const void* gy, const void* m, void* gx, int n, int h, int w, int c,
+                                        int act, void* stream);
+/* flow head: flow = 24*tanh(z) (tecogan_nets.py:80): dz = (gflow [+ gflow2]) * (24 - flow^2/24) * scale as NHWC
+ * fp16 [n,h,w,cpad]; chooses the loss scale of the FNet backward from the amax of that product (scale_ws as
+ * in tg_grad_scale_from_amax) */
+int tg_flow_head_bwd(const float* gflow, const float* gflow2, const float* flow, void* scale_ws, float target,
+                     void* dz, int n, int h, int w, int cpad, void* stream);
+/* space_to_depth backward (net_utils.py:36-47): gy [n,c*s*s,h/s,w/s] -> gx [n,c,h,w] */
+int tg_depth_to_space_nchw_f32(const float* gy, float* gx, int n, int c, int h, int w, int s, void* stream);
 
 /* ------------------------------------------------------------------------
  * Diagnostics: when a device buffer of 16*gridDim uint64 is registered, every

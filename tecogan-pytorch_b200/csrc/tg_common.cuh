@@ -103,9 +103,17 @@ __host__ __device__ static inline uint32_t tg_wtile_off(uint32_t n, uint32_t k) 
 //   acc1: in[y,x]*Wt[1,2] + in[y,x+1]*Wt[1,0]
 //   acc2: in[y,x]*Wt[2,1] + in[y+1,x]*Wt[0,1]
 //   acc3: in[y,x]*Wt[2,2] + in[y,x+1]*Wt[2,0] + in[y+1,x]*Wt[0,2] + in[y+1,x+1]*Wt[0,0]
+// conv 3x3 s2 p1 (TG_CONV_3X3_S2, the convT's data gradient): group g = ky*3+kx reads input pixel
+//   (2y+ky-1, 2x+kx-1) = pixel (y+dy, x+dx) of the input's PARITY PLANE (py,px) [plane (py,px) holds the
+//   pixels (2i+py, 2j+px)]:  k=0 -> parity 1, offset -1;  k=1 -> parity 0, offset 0;  k=2 -> parity 1, offset 0.
 struct TgGroup { int acc, dy, dx, ky, kx; };
+__host__ __device__ constexpr int tg_s2_par(int k) { return k == 1 ? 0 : 1; }
+__host__ __device__ constexpr int tg_s2_off(int k) { return k == 0 ? -1 : 0; }
+// parity plane (py*2+px) that group g of a TG_CONV_3X3_S2 layer reads
+__host__ __device__ constexpr int tg_s2_plane(int g) { return tg_s2_par(g / 3) * 2 + tg_s2_par(g % 3); }
 __host__ __device__ constexpr TgGroup tg_group(int kind, int g) {
   if (kind == TG_CONV_3X3) return TgGroup{0, g / 3 - 1, g % 3 - 1, g / 3, g % 3};
+  if (kind == TG_CONV_3X3_S2) return TgGroup{0, tg_s2_off(g / 3), tg_s2_off(g % 3), g / 3, g % 3};
   switch (g) {
     case 0: return TgGroup{0, 0, 0, 1, 1};
     case 1: return TgGroup{1, 0, 0, 1, 2};
@@ -201,4 +209,8 @@ __device__ __forceinline__ float tg_act_slope(int act) {
   return act == TG_ACT_NONE ? 1.f : (act == TG_ACT_RELU ? 0.f : 0.2f);
 }
 __device__ __forceinline__ float tg_act(float v, int act) { return fmaxf(v, v * tg_act_slope(act)); }
+// data-gradient epilogues: derivative of ReLU / LeakyReLU(0.2) taken from the stored forward OUTPUT m
+__device__ __forceinline__ float tg_dact(float m, int act) {
+  return m > 0.f ? 1.f : (act == TG_ACT_DRELU ? 0.f : 0.2f);
+}
 #endif  // __CUDACC__

@@ -12,8 +12,11 @@ namespace {
 // ------------------------------------------------------------------ weight packing
 // conv3x3: w[co][ci][ky][kx] -> tile (g=ky*3+kx, chunk=ci/64), element (row=co, k=ci%64)
 // convT  : w[ci][co][ky][kx] -> tile (g per tg_group(TG_CONVT_3X3_S2, g)), same element map
+// dgrad  : (kind = TG_CONV_3X3, dgrad = 1) the layer's roles are swapped and the taps flipped: `cout`/`cin`
+//          are the dgrad layer's (= the forward layer's cin/cout), source w_fwd[ci'][co'][2-ky][2-kx] with
+//          w_fwd laid out [cout_fwd = cin][cin_fwd = cout][3][3]
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ packed,
-                                    int kind, int cout, int cin, int cout_pad, int cin_pad) {
+                                    int kind, int cout, int cin, int cout_pad, int cin_pad, int dgrad) {
   tg_pdl_wait();
   // no early trigger: the weights this kernel writes are loaded by the next conv BEFORE its PDL wait
   const int chunks = cin_pad / 64;
@@ -28,8 +31,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
     const TgGroup gr = tg_group(kind, g);
     float v = 0.f;
     if (ci < cin && co < cout) {
-      if (kind == TG_CONV_3X3) v = w[(((size_t)co * cin + ci) * 3 + gr.ky) * 3 + gr.kx];
-      else                     v = w[(((size_t)ci * cout + co) * 3 + gr.ky) * 3 + gr.kx];
+      if (dgrad)                        v = w[(((size_t)ci * cout + co) * 3 + (2 - gr.ky)) * 3 + (2 - gr.kx)];
+      else if (kind != TG_CONVT_3X3_S2) v = w[(((size_t)co * cin + ci) * 3 + gr.ky) * 3 + gr.kx];
+      else                              v = w[(((size_t)ci * cout + co) * 3 + gr.ky) * 3 + gr.kx];
     }
     const size_t tile_bytes = (size_t)cout_pad * 128;
     unsigned char* base = reinterpret_cast<unsigned char*>(packed) + (size_t)tile * tile_bytes;
@@ -62,7 +66,7 @@ __global__ void conv_simt_kernel(tg_conv_desc d) {
   tg_pdl_wait();
   tg_pdl_trigger();
   const int chunks = d.cin / 64;
-  const int n_acc = d.kind == TG_CONV_3X3 ? 1 : 4;
+  const int n_acc = d.kind == TG_CONVT_3X3_S2 ? 4 : 1;
   const bool tapn = d.epilogue != TG_EPI_NHWC_F16;
   const int co_groups = tapn ? 1 : d.cout / 8;
   const size_t total = (size_t)d.n * d.h * d.w * n_acc * co_groups;
@@ -82,9 +86,10 @@ __global__ void conv_simt_kernel(tg_conv_desc d) {
     for (int g = 0; g < 9; ++g) {
       const TgGroup gr = tg_group(d.kind, g);
       if (gr.acc != acc) continue;
-      const int iy = yy + gr.dy, ix = xx + gr.dx;
-      if (iy < 0 || iy >= d.h || ix < 0 || ix >= d.w) continue;  // zero padding
-      const __half* px = x + (((size_t)nn * d.h + iy) * d.w + ix) * d.cin;
+      int iy = yy + gr.dy, ix = xx + gr.dx, IH = d.h, IW = d.w;
+      if (d.kind == TG_CONV_3X3_S2) { iy = 2 * yy + gr.ky - 1; ix = 2 * xx + gr.kx - 1; IH = 2 * d.h; IW = 2 * d.w; }
+      if (iy < 0 || iy >= IH || ix < 0 || ix >= IW) continue;  // zero padding
+      const __half* px = x + (((size_t)nn * IH + iy) * IW + ix) * d.cin;
       for (int ci = 0; ci < d.cin; ++ci) {
         const float xv = __half2float(px[ci]);
         if (tapn) {   // NCHW heads: tile per chunk, row = tap*4 + co, 4 real output channels max
@@ -119,7 +124,7 @@ size_t tg_packed_weight_bytes(int cin_pad, int cout_pad) {
 }
 
 static int pack_common(const float* w, int kind, int cout, int cin, void* packed, int cout_pad,
-                       int cin_pad, void* stream) {
+                       int cin_pad, void* stream, int dgrad = 0) {
   TG_REQUIRE(w && packed, TG_E_INVALID, "pack_weights: null pointer");
   TG_REQUIRE(cout > 0 && cin > 0 && cout <= cout_pad && cin <= cin_pad, TG_E_INVALID,
              "pack_weights: cout=%d cin=%d exceed pads %d/%d", cout, cin, cout_pad, cin_pad);
@@ -129,7 +134,7 @@ static int pack_common(const float* w, int kind, int cout, int cin, void* packed
   int grid = (int)((total + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   tg_launch(pack_weights_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, w, (__half*)packed, kind, cout, cin,
-            cout_pad, cin_pad);
+            cout_pad, cin_pad, dgrad);
   TG_CUDA_LAUNCH_CHECK("pack_weights");
   return TG_OK;
 }
@@ -142,6 +147,17 @@ int tg_pack_conv3x3_weights(const float* w_oihw, int cout, int cin, void* packed
 int tg_pack_convT3x3s2_weights(const float* w_iohw, int cin, int cout, void* packed, int cout_pad,
                                int cin_pad, void* stream) {
   return pack_common(w_iohw, TG_CONVT_3X3_S2, cout, cin, packed, cout_pad, cin_pad, stream);
+}
+
+int tg_pack_conv3x3_weights_dgrad(const float* w_oihw, int cout, int cin, void* packed, int cin_as_cout_pad,
+                                  int cout_as_cin_pad, void* stream) {
+  // the dgrad layer computes cin outputs from cout inputs
+  return pack_common(w_oihw, TG_CONV_3X3, cin, cout, packed, cin_as_cout_pad, cout_as_cin_pad, stream, 1);
+}
+
+int tg_pack_conv3x3s2_weights(const float* w_oihw, int cout, int cin, void* packed, int cout_pad, int cin_pad,
+                              void* stream) {
+  return pack_common(w_oihw, TG_CONV_3X3_S2, cout, cin, packed, cout_pad, cin_pad, stream);
 }
 
 size_t tg_packed_weight_bytes_tapn(int cin_pad) {
@@ -165,7 +181,7 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who);
 int tg_conv_simt(const tg_conv_desc* d, void* stream) {
   int rc = tg_conv_validate(d, "conv_simt");
   if (rc != TG_OK) return rc;
-  const int n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
+  const int n_acc = d->kind == TG_CONVT_3X3_S2 ? 4 : 1;
   const size_t total = (size_t)d->n * d->h * d->w * n_acc *
                        (d->epilogue != TG_EPI_NHWC_F16 ? 1 : d->cout / 8);
   size_t grid = (total + 127) / 128;

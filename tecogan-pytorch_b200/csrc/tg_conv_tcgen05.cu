@@ -40,6 +40,8 @@ constexpr int TH = 16, TW = 8;
 __host__ __device__ constexpr int epi_groups(int kind, int mode) {
   return (mode == 2 /*MODE_TAPN*/ || kind == TG_CONVT_3X3_S2) ? 4 : 2;
 }
+// up to four tensor maps: [0] = the NHWC input; TG_CONV_3X3_S2 reads the input's four parity planes
+struct TgMaps { CUtensorMap m[4]; };
 __host__ __device__ constexpr int conv_threads(int kind, int mode) { return 128 + 128 * epi_groups(kind, mode); }
 constexpr int kMaxStages = 8;
 constexpr uint32_t kTmemCols = 512;
@@ -93,9 +95,12 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <int KIND, int MODE, bool TIMING>
+// BWD = data-gradient instantiation: epilogue y = (acc + bias [+ residual]) * act'(mask)  (TG_ACT_DRELU /
+// TG_ACT_DLRELU02; TG_ACT_NONE = no derivative).  Kept out of the forward instantiations so their
+// register allocation and code are untouched.
+template <int KIND, int MODE, bool TIMING, bool BWD = false>
 __global__ void __launch_bounds__(conv_threads(KIND, MODE), 1)
-conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) {
+conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
@@ -118,8 +123,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
   // warps that release an accumulator buffer: the 4 warps of the group that owns the tile (for the
   // transposed conv two groups share every tile, two parity accumulators each -> 8 warps)
   const int epi_warps_active = KIND == TG_CONVT_3X3_S2 ? 8 : 4;
+  static_assert(!(KIND == TG_CONV_3X3_S2 && MODE != MODE_TAP), "the stride-2 conv runs in tap mode only");
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&map_a);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.m[0]);
+    if (KIND == TG_CONV_3X3_S2) { tma_prefetch_desc(&maps.m[1]); tma_prefetch_desc(&maps.m[2]); tma_prefetch_desc(&maps.m[3]); }
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -177,7 +186,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
             TG_ACC(tw, t0);
             mbar_expect_tx(bar_full + 8 * stage, p.a_bytes);
-            tma_load_4d(smem_stage0 + stage * p.stage_bytes, &map_a, bar_full + 8 * stage, c * 64,
+            tma_load_4d(smem_stage0 + stage * p.stage_bytes, &maps.m[0], bar_full + 8 * stage, c * 64,
                         tc.x0 + p.org_x, tc.y0 + p.org_y, tc.n);
             if (++stage == p.n_stages) { stage = 0; phase ^= 1; }
           }
@@ -192,7 +201,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
               TG_ACC(tw, t0);
               const uint32_t sa = smem_stage0 + stage * p.stage_bytes;
               mbar_expect_tx(bar_full + 8 * stage, p.a_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
-              tma_load_4d(sa, &map_a, bar_full + 8 * stage, c * 64, tc.x0 + gr.dx, tc.y0 + gr.dy, tc.n);
+              tma_load_4d(sa, &maps.m[KIND == TG_CONV_3X3_S2 ? tg_s2_plane(g) : 0], bar_full + 8 * stage, c * 64,
+                          tc.x0 + gr.dx, tc.y0 + gr.dy, tc.n);
               if (!p.b_resident)
                 bulk_load(sa + kTapABytes,
                           wglob + (size_t)(g * p.chunks + c) * p.b_tile_bytes + (size_t)tc.nb * p.b_stage_bytes,
@@ -469,7 +479,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
       // their latency hides behind the MMAs of this tile
       uint4 res[8];
       // the residual input exists only for the plain conv (validated on the host)
-      constexpr bool kCanRes = KIND == TG_CONV_3X3 && MODE != MODE_TAPN;
+      constexpr bool kCanRes = KIND != TG_CONVT_3X3_S2 && MODE != MODE_TAPN;
       const bool has_res = kCanRes && (d.epilogue == TG_EPI_NHWC_F16) && (d.residual != nullptr) && inb;
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(
@@ -477,6 +487,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
             (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
 #pragma unroll
         for (int i = 0; i < 8; i += 2) ld_global_256(rp + i, res[i], res[i + 1]);
+      }
+      uint4 msk[BWD ? 8 : 1];
+      const bool has_mask = BWD && kCanRes && d.act >= TG_ACT_DRELU && inb;
+      if (BWD && has_mask) {
+        const uint4* mp = reinterpret_cast<const uint4*>(
+            reinterpret_cast<const __half*>(d.mask) +
+            (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) ld_global_256(mp + i, msk[BWD ? i : 0], msk[BWD ? i + 1 : 0]);
       }
       mbar_wait(bar_tfull + 8 * buf, bphase, 7);
       TG_ACC(te_tfull, t_s);
@@ -513,11 +532,25 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const KParams p) 
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int cidx = i * 8 + j * 2;
-                float a0 = tg_epi_val(__uint_as_float(v[cidx]), bb[j * 2], d.act);
-                float a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bb[j * 2 + 1], d.act);
-                if (has_res) {
-                  const float2 rf = __half22float2(rh[j]);
-                  a0 += rf.x; a1 += rf.y;
+                float a0, a1;
+                if (!BWD) {
+                  a0 = tg_epi_val(__uint_as_float(v[cidx]), bb[j * 2], d.act);
+                  a1 = tg_epi_val(__uint_as_float(v[cidx + 1]), bb[j * 2 + 1], d.act);
+                  if (has_res) {
+                    const float2 rf = __half22float2(rh[j]);
+                    a0 += rf.x; a1 += rf.y;
+                  }
+                } else {
+                  a0 = __uint_as_float(v[cidx]) + bb[j * 2];
+                  a1 = __uint_as_float(v[cidx + 1]) + bb[j * 2 + 1];
+                  if (has_res) {
+                    const float2 rf = __half22float2(rh[j]);
+                    a0 += rf.x; a1 += rf.y;
+                  }
+                  if (has_mask) {
+                    const float2 mf = __half22float2(reinterpret_cast<const __half2*>(&msk[BWD ? pc * 4 + i : 0])[j]);
+                    a0 *= tg_dact(mf.x, d.act); a1 *= tg_dact(mf.y, d.act);
+                  }
                 }
                 o[j] = __floats2half2_rn(a0, a1);
               }
@@ -636,14 +669,21 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who) {
   TG_REQUIRE(d != nullptr, TG_E_INVALID, "%s: null descriptor", who);
   TG_REQUIRE(d->x && d->weights && d->bias && d->y, TG_E_INVALID, "%s: null pointer", who);
   TG_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, TG_E_INVALID, "%s: bad size n=%d h=%d w=%d", who, d->n, d->h, d->w);
-  TG_REQUIRE(d->kind == TG_CONV_3X3 || d->kind == TG_CONVT_3X3_S2, TG_E_INVALID, "%s: kind", who);
-  TG_REQUIRE(d->act >= TG_ACT_NONE && d->act <= TG_ACT_LRELU02, TG_E_INVALID, "%s: act", who);
+  TG_REQUIRE(d->kind == TG_CONV_3X3 || d->kind == TG_CONVT_3X3_S2 || d->kind == TG_CONV_3X3_S2, TG_E_INVALID,
+             "%s: kind", who);
+  TG_REQUIRE(d->act >= TG_ACT_NONE && d->act <= TG_ACT_DLRELU02, TG_E_INVALID, "%s: act", who);
+  TG_REQUIRE((d->act >= TG_ACT_DRELU) == (d->mask != nullptr), TG_E_INVALID,
+             "%s: mask must be given exactly for TG_ACT_DRELU / TG_ACT_DLRELU02", who);
+  TG_REQUIRE(!(d->act >= TG_ACT_DRELU && (d->epilogue != TG_EPI_NHWC_F16 || d->kind == TG_CONVT_3X3_S2)),
+             TG_E_UNSUPPORTED, "%s: derivative epilogues need NHWC output and a conv3x3 / conv3x3s2 layer", who);
+  TG_REQUIRE(!(d->kind == TG_CONV_3X3_S2 && d->epilogue != TG_EPI_NHWC_F16), TG_E_UNSUPPORTED,
+             "%s: conv3x3s2 needs the NHWC epilogue", who);
   TG_REQUIRE(d->cin == 64 || d->cin == 128 || d->cin == 256, TG_E_UNSUPPORTED,
              "%s: cin=%d (stored channels must be 64, 128 or 256)", who, d->cin);
   if (d->epilogue == TG_EPI_NHWC_F16) {
     TG_REQUIRE(d->cout == 64 || d->cout == 128 || d->cout == 256, TG_E_UNSUPPORTED,
                "%s: cout=%d (64, 128 or 256 for the NHWC epilogue)", who, d->cout);
-    TG_REQUIRE(!(d->residual && d->kind != TG_CONV_3X3), TG_E_UNSUPPORTED, "%s: residual with convT", who);
+    TG_REQUIRE(!(d->residual && d->kind == TG_CONVT_3X3_S2), TG_E_UNSUPPORTED, "%s: residual with convT", who);
     TG_REQUIRE(!(d->kind == TG_CONVT_3X3_S2 && d->cout != 64), TG_E_UNSUPPORTED,
                "%s: convT needs cout == 64 (4 parity accumulators in TMEM)", who);
   } else if (d->epilogue == TG_EPI_FLOW_NCHW_F32 || d->epilogue == TG_EPI_OUT_NCHW_F32) {
@@ -673,7 +713,7 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.tiles_y = tg_ceil_div(d->h, p.step_y);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
   p.chunks = d->cin / 64;
-  p.n_acc = d->kind == TG_CONV_3X3 ? 1 : 4;
+  p.n_acc = d->kind == TG_CONVT_3X3_S2 ? 4 : 1;
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
 
   // Output channels beyond 64 are split over CTAs (N = 64 per CTA): cout/64 x more CTAs on the
@@ -685,8 +725,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // NHWC: 2 groups x 2-deep ring of 16 KB store staging; TAPN: 2 groups x 2 exchange buffers
   // TAPN: one exchange buffer per epilogue group
   uint32_t staging = tapn ? (uint32_t)epi_groups(TG_CONV_3X3, MODE_TAPN) * kTapnEBytes : 0u;
-  const int hbox_w = d->kind == TG_CONV_3X3 ? TW + 2 : TW + 1;
-  const int hbox_h = d->kind == TG_CONV_3X3 ? TH + 2 : TH + 1;
+  const int hbox_w = d->kind != TG_CONVT_3X3_S2 ? TW + 2 : TW + 1;
+  const int hbox_h = d->kind != TG_CONVT_3X3_S2 ? TH + 2 : TH + 1;
   const uint32_t halo_bytes = (uint32_t)hbox_w * hbox_h * 128u;
   const uint32_t halo_stage = (halo_bytes + 1023u) & ~1023u;
   uint32_t fixed = 1024u /*align slack*/ + kHeaderBytes + staging;
@@ -695,6 +735,9 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   const bool can_resident_tap = fixed + b_total + 2u * kTapABytes <= kSmemLimit;
   int mode = d->a_mode;
   if (tapn) mode = TG_AMODE_TAP;          // placeholder; thin heads always run MODE_TAPN below
+  TG_REQUIRE(!(d->kind == TG_CONV_3X3_S2 && mode == TG_AMODE_HALO), TG_E_UNSUPPORTED,
+             "conv_tcgen05: conv3x3s2 runs in tap mode (a stride-2 view is not a UMMA descriptor)");
+  if (d->kind == TG_CONV_3X3_S2) mode = TG_AMODE_TAP;
   if (mode == TG_AMODE_AUTO) mode = can_resident_halo ? TG_AMODE_HALO : TG_AMODE_TAP;
   TG_REQUIRE(!(mode == TG_AMODE_HALO && !can_resident_halo), TG_E_UNSUPPORTED,
              "conv_tcgen05: halo mode needs the weights resident in smem (cin=%d cout=%d)", d->cin, d->cout);
@@ -743,10 +786,22 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   TG_REQUIRE(smem_bytes <= kSmemLimit, TG_E_UNSUPPORTED, "conv_tcgen05: smem %u > limit", smem_bytes);
 
   // tensor maps
-  CUtensorMap map_a;
-  rc = encode_nhwc(&map_a, d->x, d->cin, d->w, d->h, d->n, (size_t)d->cin, (size_t)d->w * d->cin,
-                   (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
-  if (rc != TG_OK) return rc;
+  TgMaps map_a;
+  if (d->kind != TG_CONV_3X3_S2) {
+    rc = encode_nhwc(&map_a.m[0], d->x, d->cin, d->w, d->h, d->n, (size_t)d->cin, (size_t)d->w * d->cin,
+                     (size_t)d->h * d->w * d->cin, 64, p.box_w, p.box_h);
+    if (rc != TG_OK) return rc;
+    map_a.m[1] = map_a.m[2] = map_a.m[3] = map_a.m[0];
+  } else {
+    // x [n,2h,2w,cin]: parity plane (py,px) = pixels (2i+py, 2j+px), each an [n,h,w,cin] strided view
+    const size_t W2 = (size_t)2 * d->w, C = (size_t)d->cin;
+    for (int pl = 0; pl < 4; ++pl) {
+      const __half* base = reinterpret_cast<const __half*>(d->x) + ((size_t)(pl >> 1) * W2 + (pl & 1)) * C;
+      rc = encode_nhwc(&map_a.m[pl], base, d->cin, d->w, d->h, d->n, 2 * C, 2 * W2 * C,
+                       (size_t)4 * d->h * d->w * C, 64, p.box_w, p.box_h);
+      if (rc != TG_OK) return rc;
+    }
+  }
 
   static TgPerDeviceOnce attr_once;
   const cudaError_t attr_err = attr_once.run([] {
@@ -761,6 +816,12 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
     TG_SET_ATTR(TG_CONV_3X3, MODE_HALO) TG_SET_ATTR(TG_CONV_3X3, MODE_TAP) TG_SET_ATTR(TG_CONV_3X3, MODE_TAPN)
     TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_HALO) TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_TAP)
 #undef TG_SET_ATTR
+#define TG_SET_ATTR_BWD(K, H)                                                                                  \
+    e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)kSmemLimit);                                                                 \
+    if (e != cudaSuccess) err = e;
+    TG_SET_ATTR_BWD(TG_CONV_3X3, MODE_HALO) TG_SET_ATTR_BWD(TG_CONV_3X3, MODE_TAP) TG_SET_ATTR_BWD(TG_CONV_3X3_S2, MODE_TAP)
+#undef TG_SET_ATTR_BWD
     return err;
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "conv_tcgen05: cudaFuncSetAttribute: %s",
@@ -777,7 +838,15 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   // allocation can never contend
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t lerr = cudaSuccess;
-  if (tapn) {
+  const bool bwd = d->act >= TG_ACT_DRELU || d->kind == TG_CONV_3X3_S2;
+  if (bwd) {
+    if (d->kind == TG_CONV_3X3_S2)
+      lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3_S2, MODE_TAP, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3_S2, MODE_TAP)), kSmemLimit, st, map_a, p);
+    else if (p.halo)
+      lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_HALO)), kSmemLimit, st, map_a, p);
+    else
+      lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAP)), kSmemLimit, st, map_a, p);
+  } else if (tapn) {
     lerr = p.dbg ? tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAPN)), kSmemLimit, st, map_a, p)
                  : tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAPN, false>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAPN)), kSmemLimit, st, map_a, p);
   } else if (d->kind == TG_CONV_3X3) {

@@ -565,9 +565,11 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   __half* o = (__half*)out;
   TG_REQUIRE(s * h >= 2 && s * w >= 2, TG_E_UNSUPPORTED, "warp_s2d_concat: HR image smaller than 2x2");
   const int fm = !lrflow ? 0 : (up_mode == TG_UP_BICUBIC ? 1 : 2);
-  // TG_WARP_SP=full: all S HR rows of an LR row per pass (the round-1 kernel shape, A/B measurements)
+  // Default: all S HR rows of an LR row per pass (12*S gathers in flight per thread, 5 CTAs/SM).
+  // TG_WARP_SP=2: two rows per pass at <= 64 registers (8 CTAs/SM) -- measured NOT faster on B200
+  // (34.3 vs 32.0 us per 4-frame launch, profiles/bench_r2a*.json): occupancy is not the limiter.
   static int sp_full = -1;
-  if (sp_full < 0) { const char* e = getenv("TG_WARP_SP"); sp_full = (e && e[0] == 'f') ? 1 : 0; }
+  if (sp_full < 0) { const char* e = getenv("TG_WARP_SP"); sp_full = (e && e[0] == '2') ? 0 : 1; }
 #define TG_WARP_LAUNCH(SS, FM)                                                                                 \
   do {                                                                                                         \
     if (sp_full) tg_launch(warp_s2d_concat_kernel<SS, FM, RY, SS>, dim3(grid), dim3(128), smem, st, hr_prev,    \

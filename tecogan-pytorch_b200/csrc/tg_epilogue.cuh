@@ -32,12 +32,23 @@ __device__ __forceinline__ void tg_epilogue_store8(const tg_conv_desc& d, int n,
     const size_t off = (((size_t)n * OH + oy) * OW + ox) * d.cout + c0;
     __align__(16) __half o[8];
     __align__(16) __half r[8];
+    __align__(16) __half m[8];
+    const bool bwd = d.act >= TG_ACT_DRELU;
     if (d.residual) *reinterpret_cast<uint4*>(r) = *reinterpret_cast<const uint4*>(
         reinterpret_cast<const __half*>(d.residual) + off);
+    if (bwd) *reinterpret_cast<uint4*>(m) = *reinterpret_cast<const uint4*>(
+        reinterpret_cast<const __half*>(d.mask) + off);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = tg_epi_val(a[j], __ldg(d.bias + c0 + j), d.act);
-      if (d.residual) v += __half2float(r[j]);
+      float v;
+      if (!bwd) {
+        v = tg_epi_val(a[j], __ldg(d.bias + c0 + j), d.act);
+        if (d.residual) v += __half2float(r[j]);
+      } else {   // data gradient: (conv + bias [+ residual]) * act'(stored output)
+        v = a[j] + __ldg(d.bias + c0 + j);
+        if (d.residual) v += __half2float(r[j]);
+        v *= tg_dact(__half2float(m[j]), d.act);
+      }
       o[j] = __float2half(v);
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y) + off) = *reinterpret_cast<const uint4*>(o);

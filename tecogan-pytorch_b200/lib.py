@@ -13,8 +13,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'tecogan_b200.h')
 
 # enums of include/tecogan_b200.h
 TG_OK = 0
-ACT_NONE, ACT_RELU, ACT_LRELU02 = 0, 1, 2
-CONV_3X3, CONVT_3X3_S2 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_DRELU, ACT_DLRELU02 = 0, 1, 2, 3, 4
+CONV_3X3, CONVT_3X3_S2, CONV_3X3_S2 = 0, 1, 2
 UP_BICUBIC, UP_BILINEAR = 0, 1
 EPI_NHWC_F16, EPI_FLOW_NCHW_F32, EPI_OUT_NCHW_F32 = 0, 1, 2
 AMODE_AUTO, AMODE_HALO, AMODE_TAP = 0, 1, 2
@@ -29,6 +29,7 @@ class ConvDesc(ctypes.Structure):
         ('cin', c_int32), ('cout', c_int32), ('cout_real', c_int32),
         ('kind', c_int32), ('act', c_int32), ('epilogue', c_int32),
         ('a_mode', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
+        ('mask', c_void_p),
     ]
 
 
@@ -37,6 +38,16 @@ class ChainLayer(ctypes.Structure):
     _fields_ = [
         ('x', c_void_p), ('weights', c_void_p), ('bias', c_void_p), ('residual', c_void_p),
         ('y', c_void_p), ('act', c_int32), ('reserved', c_int32),
+    ]
+
+
+class WgradDesc(ctypes.Structure):
+    """struct tg_wgrad_desc"""
+    _fields_ = [
+        ('x', c_void_p), ('dz', c_void_p), ('dw', c_void_p), ('scale', c_void_p),
+        ('n', c_int32), ('h', c_int32), ('w', c_int32),
+        ('cin', c_int32), ('cout', c_int32), ('cin_real', c_int32), ('cout_real', c_int32),
+        ('kind', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
     ]
 
 
@@ -71,6 +82,23 @@ _SIGNATURES = {
     'tg_float_to_uint8_nhwc': (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P]),
     'tg_downsample_bd_nchw_f32': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     'tg_debug_set_conv_timers': (c_int, [_P]),
+    # ---- training (generator backward)
+    'tg_pack_conv3x3_weights_dgrad': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P]),
+    'tg_pack_conv3x3s2_weights': (c_int, [_P, c_int, c_int, _P, c_int, c_int, _P]),
+    'tg_grad_scale_workspace_bytes': (c_size_t, []),
+    'tg_grad_scale_from_amax': (c_int, [_P, c_size_t, _P, c_size_t, c_float, _P, _P]),
+    'tg_grad_pack_nhwc_f16': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'tg_grad_unpack_nchw_f32': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    'tg_bias_grad_nhwc_f16': (c_int, [_P, c_size_t, c_int, c_int, _P, _P, _P]),
+    'tg_wgrad_tcgen05': (c_int, [ctypes.POINTER(WgradDesc), _P]),
+    'tg_wgrad_simt': (c_int, [ctypes.POINTER(WgradDesc), _P]),
+    'tg_backward_warp_bwd_nchw_f32': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'tg_warp_s2d_concat_bwd': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    'tg_upsample_bwd_nchw_f32': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P]),
+    'tg_maxpool2x2_bwd_nhwc_f16': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'tg_upsample2x_bilinear_bwd_nhwc_f16': (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    'tg_flow_head_bwd': (c_int, [_P, _P, _P, _P, c_float, _P, c_int, c_int, c_int, c_int, _P]),
+    'tg_depth_to_space_nchw_f32': (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 
 _lib = None

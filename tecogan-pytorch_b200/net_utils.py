@@ -24,6 +24,12 @@ def no_autograd(name, *tensors):
             f'autograd; call it under torch.no_grad() or detach the input explicitly')
 
 
+def _chk(t, name):
+    if not t.is_cuda:
+        raise L.TecoganB200Error(f'{name} must be a CUDA tensor: tecogan-b200 has no CPU path')
+    return t
+
+
 def _f32(t, name):
     if not t.is_cuda:
         raise L.TecoganB200Error(f'{name} must be a CUDA tensor: tecogan-b200 has no CPU path')
@@ -32,7 +38,9 @@ def _f32(t, name):
 
 def space_to_depth(x, scale):
     """Equivalent to tf.space_to_depth(): out[n,(sy*s+sx)*C+c,oh,ow] = x[n,c,oh*s+sy,ow*s+sx]."""
-    no_autograd('space_to_depth', x)
+    if needs_grad(x):
+        from .autograd import SpaceToDepthFunction
+        return SpaceToDepthFunction.apply(_chk(x, 'x'), scale)
     return ops.space_to_depth(_f32(x, 'x'), scale)
 
 
@@ -41,7 +49,11 @@ def backward_warp(x, flow, mode='bilinear', padding_mode='border'):
     align_corners=True -- the only combination the reference ever uses."""
     if mode != 'bilinear' or padding_mode != 'border':
         raise ValueError(f'Unsupported warp mode: {mode}/{padding_mode}')
-    no_autograd('backward_warp', x, flow)
+    if needs_grad(x, flow):
+        # warp loss (vsr_model.py:86) and the ST-discriminator's input builder (tecogan_nets.py:452) train
+        # through this op: scatter/gather backward kernels (tg_backward_warp_bwd_nchw_f32)
+        from .autograd import WarpFunction
+        return WarpFunction.apply(_chk(x, 'x'), _chk(flow, 'flow'))
     return ops.backward_warp(_f32(x, 'x'), _f32(flow, 'flow'))
 
 
@@ -61,7 +73,9 @@ class BicubicUpsampler(nn.Module):
             raise ValueError('tecogan-b200 BicubicUpsampler is built for a=-0.75')
 
     def forward(self, input):
-        no_autograd('BicubicUpsampler', input)
+        if needs_grad(input):
+            from .autograd import UpsampleFunction
+            return UpsampleFunction.apply(_chk(input, 'input'), self.scale_factor, L.UP_BICUBIC)
         return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BICUBIC)
 
 
@@ -73,7 +87,9 @@ class BilinearUpsampler:
         self.scale_factor = scale_factor
 
     def __call__(self, input):
-        no_autograd('bilinear upsample_func', input)
+        if needs_grad(input):
+            from .autograd import UpsampleFunction
+            return UpsampleFunction.apply(_chk(input, 'input'), self.scale_factor, L.UP_BILINEAR)
         return ops.upsample(_f32(input, 'input'), self.scale_factor, L.UP_BILINEAR)
 
 

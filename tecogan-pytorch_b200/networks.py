@@ -43,6 +43,7 @@ class _ConvCache:
 
     def __init__(self):
         self._layers = {}
+        self._dgrads = {}
 
     def get(self, key, module, kind, act, epilogue=L.EPI_NHWC_F16):
         ent = self._layers.get(key)
@@ -53,6 +54,17 @@ class _ConvCache:
             pc = ent[0]
             pc.refresh(module.weight, module.bias)
         return pc
+
+    def dgrad(self, key, module, pc=None):
+        """The data-gradient operand (ops.PackedDgrad) of the forward layer cached under `key`."""
+        if pc is None:
+            pc = self._layers[key][0]
+        ent = self._dgrads.get(key)
+        if ent is None or ent.fwd is not pc:
+            ent = self._dgrads[key] = ops.PackedDgrad(pc, module.weight)
+        else:
+            ent.refresh(module.weight)
+        return ent
 
     def refresh_all(self, force=False):
         """Re-pack (in place) every layer whose parameters changed -- captured CUDA graphs read
@@ -88,7 +100,12 @@ class FNet(nn.Module):
         """flow from x1 to x2, NCHW fp32 [n,2,8*(h//8),8*(w//8)]"""
         g1, g2 = x1, x2
         x1, x2 = _cuda_f32(x1, 'x1'), _cuda_f32(x2, 'x2')
-        no_autograd('FNet.forward', g1, g2, *(self.parameters() if self.training else ()))
+        no_autograd('FNet.forward (input gradient)', g1, g2)
+        if self.training and needs_grad(*self.parameters()):
+            # trained through (FRNet.forward_sequence has its own fused path; this is the bare call the
+            # ST-discriminator makes, tecogan_nets.py:420): forward + backward on the library's kernels
+            from .autograd import FNetFunction
+            return FNetFunction.apply(self, x1, x2, *self.parameters())
         a = ops.pack_pair(x1, x2)                       # cat + NHWC fp16 (c64)
         for name, _, _ in self.ENC:
             a = self._conv(name, 0, _LRELU)(a)
@@ -261,12 +278,23 @@ class FRNet(BaseSequenceGenerator):
     def forward_sequence(self, lr_data):
         """lr_data ntchw -> dict(hr_data, hr_flow, lr_prev, lr_curr, lr_flow), reference :174-225.
 
-        Forward only: the backward kernels are the next row of the scope table,
-        so calling this with autograd enabled is an error rather than a silent detach."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                'tecogan-b200 FRNet.forward_sequence is forward-only in this build (generator '
-                'backward kernels are not built yet); call it under torch.no_grad().')
+        Under autograd (training) the whole sequence is ONE autograd node (autograd.SequenceFunction):
+        forward and backward -- dgrad / wgrad of every conv, the warp's scatter/gather, pool / upsample
+        / tanh derivatives -- run on the library's kernels and the parameters receive fp32 gradients,
+        so VSRModel.train / VSRGANModel.train (and DDP's gradient all-reduce) work unchanged.
+        lr_data is data: no gradient is produced for it."""
+        no_autograd('FRNet.forward_sequence (lr_data gradient)', lr_data)
+        if needs_grad(*self.parameters()):
+            from .autograd import SequenceFunction
+            lr_data = _cuda_f32(lr_data, 'lr_data')
+            n, t, c, lr_h, lr_w = lr_data.shape
+            hr_data, hr_flow, lr_flow = SequenceFunction.apply(self, lr_data, *self.parameters())
+            return {
+                'hr_data': hr_data, 'hr_flow': hr_flow,
+                'lr_prev': lr_data[:, :-1].reshape(n * (t - 1), c, lr_h, lr_w),
+                'lr_curr': lr_data[:, 1:].reshape(n * (t - 1), c, lr_h, lr_w),
+                'lr_flow': lr_flow,
+            }
         lr_data = _cuda_f32(lr_data, 'lr_data')
         n, t, c, lr_h, lr_w = lr_data.shape
         s = self.scale

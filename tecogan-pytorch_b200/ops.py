@@ -351,3 +351,251 @@ def float_to_uint8_nhwc(x, y=None):
     L.check(L.load().tg_float_to_uint8_nhwc(_ptr(x), _ptr(y), n, c, h, w, _stream()),
             'tg_float_to_uint8')
     return y
+
+
+# ============================================================================ training (backward) ops
+class GradScale:
+    """Device-resident loss scale {scale, 1/scale} of the fp16 gradient path (tg_grad_scale_from_amax /
+    tg_flow_head_bwd choose it on the device -- no host round trip)."""
+
+    TARGET = 256.0      # amax of the incoming gradient is scaled to ~2^8: 2^8 of headroom below fp16 max
+
+    def __init__(self, device):
+        self.ws = torch.zeros(4, dtype=torch.float32, device=device)       # 16 bytes, zeroed once
+
+    def from_amax(self, a, b=None, target=None):
+        _req(a, torch.float32, 'grad')
+        if b is not None:
+            _req(b, torch.float32, 'grad')
+        L.check(L.load().tg_grad_scale_from_amax(_ptr(a), a.numel(), _ptr(b), b.numel() if b is not None else 0,
+                                                 ctypes.c_float(target or self.TARGET), _ptr(self.ws), _stream()),
+                'tg_grad_scale_from_amax')
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += 1            # two kernels per call
+        return self
+
+    @property
+    def ptr(self):
+        return ctypes.c_void_p(self.ws.data_ptr())
+
+
+def _scale_ptr(scale):
+    return scale.ptr if scale is not None else ctypes.c_void_p(0)
+
+
+class PackedDgrad:
+    """Data-gradient operand of a conv layer: the same tcgen05 implicit GEMM with the roles of the
+    channel dimensions swapped -- conv3x3: taps flipped (tg_pack_conv3x3_weights_dgrad); convT3x3s2: a
+    stride-2 conv over the output gradient (TG_CONV_3X3_S2).  Built from the forward PackedConv."""
+
+    def __init__(self, fwd, weight):
+        self.fwd = fwd
+        self.kind = L.CONV_3X3 if fwd.kind == L.CONV_3X3 else L.CONV_3X3_S2
+        self.cin = pad64(fwd.cout_real)        # channels of dz
+        self.cout = fwd.cin                    # channels of the input gradient (stored)
+        self.packed = None
+        self._ver = None
+        self.refresh(weight)
+
+    def refresh(self, weight, force=False):
+        ver = (weight._version, weight.data_ptr())
+        if ver == self._ver and not force:
+            return
+        lib = L.load()
+        w = _req(weight.detach(), torch.float32, 'weight', 4)
+        if self.packed is None:
+            self.packed = torch.empty(lib.tg_packed_weight_bytes(self.cin, self.cout), dtype=torch.uint8, device=w.device)
+            self.bias = torch.zeros(self.cout, dtype=torch.float32, device=w.device)
+        f = self.fwd
+        if self.kind == L.CONV_3X3:
+            rc = lib.tg_pack_conv3x3_weights_dgrad(_ptr(w), f.cout_real, f.cin_real, _ptr(self.packed), self.cout,
+                                                   self.cin, _stream())
+        else:   # nn.ConvTranspose2d weight [cin,cout,3,3] read as OIHW with out = cin, in = cout
+            rc = lib.tg_pack_conv3x3s2_weights(_ptr(w), f.cin_real, f.cout_real, _ptr(self.packed), self.cout,
+                                               self.cin, _stream())
+        L.check(rc, 'tg_pack_weights (dgrad)')
+        self._ver = ver
+
+    def __call__(self, dz, y=None, residual=None, mask=None, mask_act=L.ACT_NONE, impl=None):
+        """dz NHWC fp16 [n,oh,ow,cin] -> gradient w.r.t. the layer input [n,h,w,cout];
+        y = (conv [+ residual]) * act'(mask)."""
+        _req(dz, torch.float16, 'dz', 4)
+        n, oh, ow, c = dz.shape
+        if c != self.cin:
+            raise L.TecoganB200Error(f'dgrad: dz has {c} channels, expected {self.cin}')
+        if self.kind == L.CONV_3X3_S2:
+            if oh % 2 or ow % 2:
+                raise L.TecoganB200Error('dgrad of the transposed conv needs even output sizes')
+            h, w = oh // 2, ow // 2
+        else:
+            h, w = oh, ow
+        if y is None:
+            y = torch.empty((n, h, w, self.cout), dtype=torch.float16, device=dz.device)
+        for t, nm in ((y, 'dx'), (residual, 'residual'), (mask, 'mask')):
+            if t is not None:
+                _req(t, torch.float16, nm, 4)
+                if tuple(t.shape) != (n, h, w, self.cout):
+                    raise L.TecoganB200Error(f'dgrad: {nm} shape {tuple(t.shape)} != {(n, h, w, self.cout)}')
+        if (mask is not None) != (mask_act in (L.ACT_RELU, L.ACT_LRELU02)):
+            raise L.TecoganB200Error('dgrad: mask and mask_act (RELU / LRELU02) go together')
+        d = L.ConvDesc()
+        d.x, d.weights, d.bias = dz.data_ptr(), self.packed.data_ptr(), self.bias.data_ptr()
+        d.residual = residual.data_ptr() if residual is not None else None
+        d.mask = mask.data_ptr() if mask is not None else None
+        d.y = y.data_ptr()
+        d.n, d.h, d.w, d.cin, d.cout, d.cout_real = n, h, w, self.cin, self.cout, self.cout
+        d.kind, d.epilogue = self.kind, L.EPI_NHWC_F16
+        d.act = {L.ACT_NONE: L.ACT_NONE, L.ACT_RELU: L.ACT_DRELU, L.ACT_LRELU02: L.ACT_DLRELU02}[mask_act]
+        d.a_mode = L.AMODE_AUTO
+        impl = impl or default_conv_impl()
+        lib = L.load()
+        if impl == 'tcgen05':
+            L.check(lib.tg_conv_tcgen05(ctypes.byref(d), _stream()), 'tg_conv_tcgen05 (dgrad)')
+        else:
+            L.check(lib.tg_conv_simt(ctypes.byref(d), _stream()), 'tg_conv_simt (dgrad)')
+        return y
+
+
+def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0):
+    """dw (fp32, the parameter's layout, pre-zeroed or accumulating) += 1/scale * x (*) dz for the
+    forward layer `fwd` (PackedConv): x = its NHWC fp16 input, dz = gradient of its pre-activation
+    output (NHWC fp16, pad64(cout_real) channels)."""
+    _req(x, torch.float16, 'x', 4)
+    _req(dz, torch.float16, 'dz', 4)
+    _req(dw, torch.float32, 'dw', 4)
+    n, h, w, cin = x.shape
+    up = 2 if fwd.kind == L.CONVT_3X3_S2 else 1
+    cout = pad64(fwd.cout_real)
+    if cin != fwd.cin or tuple(dz.shape) != (n, up * h, up * w, cout):
+        raise L.TecoganB200Error(f'wgrad: shapes x {tuple(x.shape)} dz {tuple(dz.shape)} do not fit the layer')
+    want = (fwd.cout_real, fwd.cin_real, 3, 3) if fwd.kind == L.CONV_3X3 else (fwd.cin_real, fwd.cout_real, 3, 3)
+    if tuple(dw.shape) != want:
+        raise L.TecoganB200Error(f'wgrad: dw shape {tuple(dw.shape)} != {want}')
+    d = L.WgradDesc()
+    d.x, d.dz, d.dw = x.data_ptr(), dz.data_ptr(), dw.data_ptr()
+    d.scale = scale.ws.data_ptr() if scale is not None else None
+    d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
+    d.cin_real, d.cout_real, d.kind, d.max_ctas, d.reserved = fwd.cin_real, fwd.cout_real, fwd.kind, max_ctas, 0
+    lib = L.load()
+    impl = impl or default_conv_impl()
+    if impl == 'tcgen05':
+        L.check(lib.tg_wgrad_tcgen05(ctypes.byref(d), _stream()), 'tg_wgrad_tcgen05')
+    else:
+        L.check(lib.tg_wgrad_simt(ctypes.byref(d), _stream()), 'tg_wgrad_simt')
+    return dw
+
+
+def bias_grad(dz, db, scale=None):
+    """db (fp32 [c_real]) += 1/scale * sum over pixels of dz[..., :c_real]"""
+    _req(dz, torch.float16, 'dz', 4)
+    _req(db, torch.float32, 'db', 1)
+    c = dz.shape[-1]
+    L.check(L.load().tg_bias_grad_nhwc_f16(_ptr(dz), dz.numel() // c, c, db.numel(), _scale_ptr(scale), _ptr(db),
+                                           _stream()), 'tg_bias_grad')
+    return db
+
+
+def grad_pack(a, b=None, scale=None, cpad=64, y=None):
+    """(a [+ b]) * scale : NCHW fp32 -> NHWC fp16 (cpad channels)"""
+    _req(a, torch.float32, 'grad', 4)
+    if b is not None:
+        _req(b, torch.float32, 'grad', 4)
+    n, c, h, w = a.shape
+    if y is None:
+        y = torch.empty((n, h, w, cpad), dtype=torch.float16, device=a.device)
+    L.check(L.load().tg_grad_pack_nhwc_f16(_ptr(a), _ptr(b), _scale_ptr(scale), _ptr(y), n, c, h, w, cpad, _stream()),
+            'tg_grad_pack')
+    return y
+
+
+def grad_unpack(x, c, scale=None, c_offset=0, y=None, accumulate=False):
+    """channels [c_offset, c_offset+c) of NHWC fp16 -> NCHW fp32 / scale"""
+    _req(x, torch.float16, 'x', 4)
+    n, h, w, cpad = x.shape
+    if y is None:
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(L.load().tg_grad_unpack_nchw_f32(_ptr(x), _scale_ptr(scale), _ptr(y), n, c, h, w, cpad, c_offset,
+                                             int(accumulate), _stream()), 'tg_grad_unpack')
+    return y
+
+
+def backward_warp_bwd(x, flow, gy, need_x=True, need_flow=True):
+    """-> (gx, gflow) of backward_warp(x, flow) given gy; outputs not needed are None"""
+    _req(x, torch.float32, 'x', 4)
+    _req(flow, torch.float32, 'flow', 4)
+    _req(gy, torch.float32, 'gy', 4)
+    n, c, h, w = x.shape
+    gx = torch.zeros_like(x) if need_x else None              # scatter-add target
+    gf = torch.empty_like(flow) if need_flow else None
+    L.check(L.load().tg_backward_warp_bwd_nchw_f32(_ptr(x), _ptr(flow), _ptr(gy), _ptr(gx), _ptr(gf), n, c, h, w,
+                                                   _stream()), 'tg_backward_warp_bwd')
+    return gx, gf
+
+
+def warp_s2d_concat_bwd(gx, hr_prev, hr_flow, scale_factor, d_hr_prev=None, d_hr_flow=None, scale=None):
+    """gradient of warp_s2d_concat_hrflow: accumulates into d_hr_prev (fp32 NCHW), stores d_hr_flow"""
+    _req(gx, torch.float16, 'gx', 4)
+    _req(hr_prev, torch.float32, 'hr_prev', 4)
+    _req(hr_flow, torch.float32, 'hr_flow', 4)
+    n, h, w, cpad = gx.shape
+    c = hr_prev.shape[1]
+    L.check(L.load().tg_warp_s2d_concat_bwd(_ptr(gx), _ptr(hr_prev), _ptr(hr_flow), _scale_ptr(scale), _ptr(d_hr_prev),
+                                            _ptr(d_hr_flow), n, c, h, w, scale_factor, cpad, _stream()),
+            'tg_warp_s2d_concat_bwd')
+
+
+def upsample_bwd(gy, scale_factor, up_mode, mul=1.0, gx=None, accumulate=False):
+    _req(gy, torch.float32, 'gy', 4)
+    n, c, H, W = gy.shape
+    h, w = H // scale_factor, W // scale_factor
+    if gx is None:
+        gx = torch.empty((n, c, h, w), dtype=torch.float32, device=gy.device)
+    L.check(L.load().tg_upsample_bwd_nchw_f32(_ptr(gy), _ptr(gx), n, c, h, w, scale_factor, up_mode, ctypes.c_float(mul),
+                                              int(accumulate), _stream()), 'tg_upsample_bwd')
+    return gx
+
+
+def maxpool2x2_bwd(x, gy, act, gx=None):
+    _req(x, torch.float16, 'x', 4)
+    _req(gy, torch.float16, 'gy', 4)
+    n, h, w, c = x.shape
+    if gx is None:
+        gx = torch.empty_like(x)
+    L.check(L.load().tg_maxpool2x2_bwd_nhwc_f16(_ptr(x), _ptr(gy), _ptr(gx), n, h, w, c, act, _stream()),
+            'tg_maxpool2x2_bwd')
+    return gx
+
+
+def upsample2x_bwd(gy, m, act, gx=None):
+    _req(gy, torch.float16, 'gy', 4)
+    _req(m, torch.float16, 'm', 4)
+    n, h, w, c = m.shape
+    if gx is None:
+        gx = torch.empty_like(m)
+    L.check(L.load().tg_upsample2x_bilinear_bwd_nhwc_f16(_ptr(gy), _ptr(m), _ptr(gx), n, h, w, c, act, _stream()),
+            'tg_upsample2x_bwd')
+    return gx
+
+
+def flow_head_bwd(gflow, flow, scale, gflow2=None, cpad=64, dz=None):
+    """dz (NHWC fp16) of the 24*tanh flow head; also chooses `scale` (GradScale) for the FNet backward"""
+    _req(gflow, torch.float32, 'gflow', 4)
+    _req(flow, torch.float32, 'flow', 4)
+    n, _, h, w = flow.shape
+    if dz is None:
+        dz = torch.empty((n, h, w, cpad), dtype=torch.float16, device=flow.device)
+    L.check(L.load().tg_flow_head_bwd(_ptr(gflow), _ptr(gflow2), _ptr(flow), scale.ptr, ctypes.c_float(scale.TARGET),
+                                      _ptr(dz), n, h, w, cpad, _stream()), 'tg_flow_head_bwd')
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 2
+    return dz
+
+
+def depth_to_space(gy, scale_factor):
+    _req(gy, torch.float32, 'gy', 4)
+    n, cs, oh, ow = gy.shape
+    c = cs // (scale_factor * scale_factor)
+    gx = torch.empty((n, c, oh * scale_factor, ow * scale_factor), dtype=torch.float32, device=gy.device)
+    L.check(L.load().tg_depth_to_space_nchw_f32(_ptr(gy), _ptr(gx), n, c, oh * scale_factor, ow * scale_factor,
+                                                scale_factor, _stream()), 'tg_depth_to_space')
+    return gx

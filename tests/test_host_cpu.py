@@ -35,16 +35,35 @@ def test_library_exports_every_header_symbol():
     # the ctypes binding covers exactly the header
     assert sorted(L.exported_symbols()) == names
     T.load_library()
-    assert L.load().tg_version() == 1
+    assert L.load().tg_version() == 2          # ABI 2: tg_conv_desc.mask + the backward entry points
     assert L.load().tg_packed_weight_bytes(64, 64) == 9 * 64 * 128
     assert L.load().tg_packed_weight_bytes(256, 256) == 9 * 4 * 256 * 128
     assert L.load().tg_packed_weight_bytes(60, 64) == 0
 
 
 def test_conv_desc_struct_layout_matches_header():
-    # 5 pointers + 12 int32 (see struct tg_conv_desc)
-    assert ctypes.sizeof(L.ConvDesc) == 5 * 8 + 12 * 4
+    # 5 pointers + 12 int32 + the mask pointer (see struct tg_conv_desc)
+    assert ctypes.sizeof(L.ConvDesc) == 5 * 8 + 12 * 4 + 8
     assert L.ConvDesc.n.offset == 40 and L.ConvDesc.max_ctas.offset == 40 + 10 * 4
+    assert L.ConvDesc.mask.offset == 88
+    # struct tg_wgrad_desc: 4 pointers + 10 int32
+    assert ctypes.sizeof(L.WgradDesc) == 4 * 8 + 10 * 4 and L.WgradDesc.n.offset == 32
+
+
+def test_backward_entry_points_reject_bad_arguments_without_a_gpu():
+    lib = L.load()
+    assert lib.tg_grad_scale_workspace_bytes() == 16
+    w = L.WgradDesc()
+    assert lib.tg_wgrad_tcgen05(ctypes.byref(w), None) == -1 and b'null' in lib.tg_last_error_string()
+    w.x = w.dz = w.dw = 16
+    w.n, w.h, w.w, w.cin, w.cout, w.cin_real, w.cout_real = 1, 8, 8, 48, 64, 48, 64
+    assert lib.tg_wgrad_tcgen05(ctypes.byref(w), None) == -2                    # stored cin must be 64/128/256
+    d = L.ConvDesc()
+    d.x = d.weights = d.bias = d.y = 16
+    d.n, d.h, d.w, d.cin, d.cout, d.act = 1, 8, 8, 64, 64, L.ACT_DRELU
+    assert lib.tg_conv_tcgen05(ctypes.byref(d), None) == -1 and b'mask' in lib.tg_last_error_string()
+    assert lib.tg_upsample_bwd_nchw_f32(ctypes.c_void_p(16), ctypes.c_void_p(16), 1, 2, 8, 8, 3, 0, 1.0, 0, None) == -2
+    assert lib.tg_warp_s2d_concat_bwd(None, None, None, None, None, None, 1, 3, 8, 8, 4, 64, None) == -1
 
 
 def test_chain_layer_struct_and_argument_checks():

@@ -133,6 +133,30 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream);
 int tg_conv_simt(const tg_conv_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------
+ * SRNet tail in one launch: last nn.ConvTranspose2d(64,64,3,2,1,op=1) + ReLU -> conv_out (64 -> out_nc)
+ * -> + upsample_func(lr_curr) (tecogan_nets.py:119-131,143-145), optionally also float32_to_uint8 +
+ * CHW->HWC (data_utils.py:80-87, tecogan_nets.py:278-281).  The 64-channel HR map only exists as one
+ * 32x16-pixel tile in shared memory instead of a round trip through HBM.
+ * ---------------------------------------------------------------------- */
+typedef struct tg_tail_desc {
+  const void* x;        /* input of the transposed conv, NHWC fp16 [n,h,w,64]                       */
+  const void* w_up;     /* tg_pack_convT3x3s2_weights(cout_pad=64, cin_pad=64)                      */
+  const float* b_up;    /* fp32 [64]                                                                */
+  const void* w_out;    /* tg_pack_conv3x3_weights_tapn(cin_pad=64)                                 */
+  const float* b_out;   /* fp32 [cout_real]                                                         */
+  const float* lr;      /* lr_curr NCHW fp32 [n,cout_real,2h/lr_scale,2w/lr_scale] or NULL          */
+  float* y;             /* NCHW fp32 [n,cout_real,2h,2w]                                            */
+  uint8_t* y_u8;        /* NHWC uint8 [n,2h,2w,cout_real] (round-half-even, clip) or NULL           */
+  int32_t n, h, w;      /* of the transposed conv's input                                           */
+  int32_t cout_real;    /* 1..3                                                                     */
+  int32_t lr_scale;     /* 2 or 4: output size / lr size                                            */
+  int32_t up_mode;      /* TG_UP_*                                                                  */
+  int32_t max_ctas;     /* 0 = one persistent CTA per SM                                            */
+  int32_t reserved;     /* must be 0                                                                */
+} tg_tail_desc;
+int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------
  * A chain of 64->64 3x3 convolutions (SRNet conv_in + the residual blocks,
  * tecogan_nets.py:92-100, 111-116, 139-141) as ONE persistent launch: every CTA walks all
  * layers over its fixed set of 16x8 tiles; a tile of layer l starts as soon as the (up to 9)

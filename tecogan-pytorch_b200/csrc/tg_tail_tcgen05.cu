@@ -1,0 +1,485 @@
+// SRNet tail in ONE kernel (sm_100a): last ConvTranspose2d(64,64,3,2,1,op=1) + ReLU  ->  conv_out 3x3
+// (64 -> out_nc <= 4)  ->  + upsample_func(lr_curr)  ->  fp32 NCHW frame (+ uint8 NHWC frame).
+//
+// Replaces nn.ConvTranspose2d+ReLU, nn.Conv2d and `out += self.upsample_func(lr_curr)`
+// (tecogan_nets.py:119-131,143-145) and float32_to_uint8 + CHW->HWC (data_utils.py:80-87,
+// tecogan_nets.py:278-281).  As separate kernels the 64-channel HR map (351 MB for four 536x1280
+// frames) is written to and read back from HBM -- 24 % of the round-1 step for 16 % of its FLOPs;
+// here it only ever exists as one 32x16-pixel tile in shared memory.
+//
+// One CTA walks tiles of 16x8 pixels of the transposed conv's INPUT (17x9 halo box by TMA):
+//   1. transposed conv = 4 parity accumulators in TMEM (1/2/2/4 taps, K = 64 per tap), as in
+//      tg_conv_tcgen05.cu; issued as two halves (parities 0,1 | 2,3) with their own barriers.
+//   2. epilogue A (8 warps): TMEM -> +bias, ReLU, fp16 -> the HR tile in shared memory, stored directly
+//      in the UMMA operand layout (K-major, 128B swizzle): block q = parity (py,px), row m = input
+//      pixel (m>>3, m&7) = HR pixel (2*(m>>3)+py, 2*(m&7)+px); pixels outside the image are ZERO
+//      (conv_out's zero padding).
+//   3. conv_out as "tap-major N" MMAs on that tile: D2[pixel][tap*4+co] = x[pixel] . W[tap][co]
+//      (N = 48, four K=16 MMAs per 128-pixel block).
+//   4. epilogue B (4 warps): the 3x3 shift-add  out[P] = sum_taps D2[P+off(tap)][tap].  A thread owns
+//      the 2x2 HR quad of its input pixel in all four blocks: 16 of the 36 terms stay in its registers,
+//      the rest are pre-summed per receiving pixel and handed to the 8 neighbouring quads through a
+//      24 KB exchange buffer (12 float4 per thread instead of 36); + bias + upsample_func(lr_curr)
+//      (one 4x4 LR neighbourhood per quad) -> fp32 NCHW and uint8 NHWC stores.
+//   Valid outputs per tile: 30x14 HR pixels (tiles advance by 15x7 input pixels; the transposed conv is
+//   recomputed on the one-pixel ring, 1.22x).  Issue order of the MMA warp is software-pipelined --
+//   ConvT(i).p0, conv_out(i-1).b23, ConvT(i).p1, conv_out(i).b01 -- so the tensor pipe always has the
+//   other half's MMAs queued while an epilogue-A half converts, and the in-order pipe itself protects
+//   the HR tile against being overwritten before conv_out has read it.
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "tg_common.cuh"
+#include "tg_tcgen05.cuh"
+
+namespace {
+
+constexpr int TH = 16, TW = 8;
+constexpr int kStepY = 15, kStepX = 7;          // input pixels a tile advances by
+constexpr int kThreads = 512;                    // 4 control warps + 8 epilogue-A + 4 epilogue-B
+constexpr int kBoxW = TW + 1, kBoxH = TH + 1;    // 17 x 9 halo box, origin at the tile's first pixel
+constexpr uint32_t kHaloBytes = kBoxW * kBoxH * 128;           // 19584
+constexpr uint32_t kStageBytes = (kHaloBytes + 1023u) & ~1023u;  // 20480
+constexpr int kStages = 2;
+constexpr uint32_t kWtBytes = 9 * 64 * 128;      // transposed-conv weights, 9 tap tiles of [64][64]
+constexpr uint32_t kWoBytes = TG_TAPN_ROWS * 128;  // conv_out weights, [48 rows = tap*4+co][64]
+constexpr uint32_t kHrBlock = 128 * 128;         // one parity block of the HR tile: 128 pixels x 128 B
+constexpr uint32_t kExBytes = 128 * 12 * 16;     // exchange buffer: 12 float4 per quad
+constexpr uint32_t kOffWt = 2048;
+constexpr uint32_t kOffWo = kOffWt + kWtBytes;                 // 75776
+constexpr uint32_t kOffStage = kOffWo + kWoBytes;              // 81920 (1024-aligned)
+constexpr uint32_t kOffHr = kOffStage + kStages * kStageBytes; // 122880 (1024-aligned)
+constexpr uint32_t kOffEx = kOffHr + 4 * kHrBlock;             // 188416
+constexpr uint32_t kSmemBytes = kOffEx + kExBytes + 1024;      // + alignment slack = 214016
+static_assert(kOffStage % 1024 == 0 && kOffHr % 1024 == 0, "swizzled regions need 1024-byte alignment");
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kD2Col = 256;                 // D2 block q at columns 256 + 64*q (48 used)
+
+struct TailParams {
+  CUtensorMap map_x;
+  const unsigned char* w_up;
+  const unsigned char* w_out;
+  const float* b_up;
+  const float* b_out;
+  const float* lr;           // lr_curr NCHW fp32 [n,cout_real,lh,lw] or null
+  float* y;                  // NCHW fp32 [n,cout_real,2h,2w]
+  uint8_t* y_u8;             // NHWC uint8 [n,2h,2w,cout_real] or null
+  int n, h, w, cout_real;
+  int lr_scale, up_mode, lh, lw;
+  int tiles_x, tiles_y, num_tiles;
+  uint32_t idesc_up, idesc_out;
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t q8(float v) { return (uint32_t)fminf(fmaxf(rintf(v * 255.f), 0.f), 255.f); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t bar_full = base;              // [2] halo stage landed
+  const uint32_t bar_empty = base + 16;        // [2] halo stage consumed
+  const uint32_t bar_w = base + 32;            // weights resident
+  const uint32_t bar_tfull = base + 40;        // [2] ConvT accumulator half complete
+  const uint32_t bar_tempty = base + 56;       // [2] ... drained by epilogue A
+  const uint32_t bar_hrfull = base + 72;       // [2] HR-tile half written by epilogue A
+  const uint32_t bar_d2full = base + 88;       // conv_out accumulators complete
+  const uint32_t bar_d2empty = base + 96;      // ... drained by epilogue B
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 128);
+  float* bias_up_s = reinterpret_cast<float*>(sm + 1024);
+  float* bias_out_s = reinterpret_cast<float*>(sm + 1024 + 256);
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.map_x);
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    mbar_init(bar_w, 1);
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(bar_tfull + 8 * h, 1);
+      mbar_init(bar_tempty + 8 * h, 4);
+      mbar_init(bar_hrfull + 8 * h, 4);
+    }
+    mbar_init(bar_d2full, 1);
+    mbar_init(bar_d2empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  // resident weights do not depend on the previous kernel: load them before the PDL wait
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(bar_w, kWtBytes + kWoBytes);
+    for (int g = 0; g < 9; ++g) bulk_load(base + kOffWt + g * 8192u, p.w_up + (size_t)g * 8192u, 8192u, bar_w);
+    bulk_load(base + kOffWo, p.w_out, kWoBytes, bar_w);
+  }
+  tg_pdl_wait();
+  tg_pdl_trigger();
+  for (int i = threadIdx.x; i < 64; i += kThreads) bias_up_s[i] = p.b_up[i];
+  if (threadIdx.x < 4) bias_out_s[threadIdx.x] = threadIdx.x < p.cout_real ? p.b_out[threadIdx.x] : 0.f;
+  __syncthreads();
+
+  const int per_img = p.tiles_x * p.tiles_y;
+  const int H = 2 * p.h, W = 2 * p.w;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (uint32_t)(it >> 1) & 1u;
+        const int img = tile / per_img, r = tile - img * per_img;
+        const int y0 = (r / p.tiles_x) * kStepY - 1, x0 = (r % p.tiles_x) * kStepX - 1;
+        mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+        mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
+        tma_load_4d(base + kOffStage + stage * kStageBytes, &p.map_x, bar_full + 8 * stage, 0, x0, y0, img);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ MMA issuer
+    mbar_wait(bar_w, 0, 2);
+    const uint64_t a_hi = make_sdesc(0, (uint32_t)kBoxW * 128u);     // halo views: 8-row groups one box row apart
+    const uint64_t k_hi = make_sdesc(0, 1024u);                      // weights / HR tile blocks: dense 8-row groups
+    const uint32_t wt16 = ((base + kOffWt) & 0x3FFFFu) >> 4;
+    const uint32_t wo16 = ((base + kOffWo) & 0x3FFFFu) >> 4;
+    const uint32_t hr16 = ((base + kOffHr) & 0x3FFFFu) >> 4;
+    auto issue_convt = [&](uint32_t sa16, int g_lo, int g_hi) {
+#pragma unroll
+      for (int g = 0; g < 9; ++g) {
+        if (g < g_lo || g >= g_hi) continue;
+        const TgGroup gr = tg_group(TG_CONVT_3X3_S2, g);
+        const bool first_of_acc = (g == 0) || (tg_group(TG_CONVT_3X3_S2, g > 0 ? g - 1 : 0).acc != gr.acc);
+        const uint32_t off = (uint32_t)(gr.dy * kBoxW + gr.dx) * 8u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + (uint32_t)gr.acc * 64u, a_hi | (uint64_t)(sa16 + off + 2u * k),
+                   k_hi | (uint64_t)(wt16 + (uint32_t)g * 512u + 2u * k), p.idesc_up, (first_of_acc && k == 0) ? 0u : 1u);
+      }
+    };
+    auto issue_convout = [&](int q_lo) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + kD2Col + (uint32_t)(q_lo + q) * 64u, k_hi | (uint64_t)(hr16 + (uint32_t)(q_lo + q) * 1024u + 2u * k),
+                   k_hi | (uint64_t)(wo16 + 2u * k), p.idesc_out, k == 0 ? 0u : 1u);
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int stage = it & 1;
+      const uint32_t sph = (uint32_t)(it >> 1) & 1u, tph = (uint32_t)it & 1u;
+      const uint32_t sa16 = ((base + kOffStage + stage * kStageBytes) & 0x3FFFFu) >> 4;
+      mbar_wait(bar_full + 8 * stage, sph, 3);
+      mbar_wait(bar_tempty + 0, tph ^ 1, 4);
+      tc_fence_after();
+      if (elect_one_sync()) { issue_convt(sa16, 0, 3); umma_commit(bar_tfull + 0); }
+      __syncwarp();
+      if (it > 0) {                                   // second half of conv_out of the previous tile
+        mbar_wait(bar_hrfull + 8, (uint32_t)(it - 1) & 1u, 5);
+        tc_fence_after();
+        if (elect_one_sync()) { issue_convout(2); umma_commit(bar_d2full); }
+        __syncwarp();
+      }
+      mbar_wait(bar_tempty + 8, tph ^ 1, 4);
+      tc_fence_after();
+      if (elect_one_sync()) { issue_convt(sa16, 3, 9); umma_commit(bar_tfull + 8); umma_commit(bar_empty + 8 * stage); }
+      __syncwarp();
+      mbar_wait(bar_hrfull + 0, tph, 5);
+      mbar_wait(bar_d2empty, tph ^ 1, 6);
+      tc_fence_after();
+      if (elect_one_sync()) issue_convout(0);
+      __syncwarp();
+    }
+    if (it > 0) {
+      mbar_wait(bar_hrfull + 8, (uint32_t)(it - 1) & 1u, 5);
+      tc_fence_after();
+      if (elect_one_sync()) { issue_convout(2); umma_commit(bar_d2full); }
+      __syncwarp();
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ============================================================ epilogue A: ConvT accumulators -> HR tile (smem)
+    const int half = (warp - 4) >> 2;         // parities {0,1} or {2,3}
+    const int q = warp & 3;
+    const int m = q * 32 + lane;              // TMEM lane = input pixel of the tile
+    const int ty = m >> 3, tx = m & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / per_img, r = tile - img * per_img;
+      const int y0 = (r / p.tiles_x) * kStepY - 1, x0 = (r % p.tiles_x) * kStepX - 1;
+      (void)img;
+      mbar_wait(bar_tfull + 8 * half, (uint32_t)it & 1u, 7);
+      tc_fence_after();
+#pragma unroll
+      for (int a2 = 0; a2 < 2; ++a2) {
+        const int acc = half * 2 + a2;
+        const int Y = 2 * (y0 + ty) + (acc >> 1), X = 2 * (x0 + tx) + (acc & 1);
+        const bool inside = Y >= 0 && Y < H && X >= 0 && X < W;
+        uint8_t* row = sm + kOffHr + (uint32_t)acc * kHrBlock + (uint32_t)m * 128u;
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t)acc * 64u + pc * 32 + ((uint32_t)(q * 32) << 16), v);
+          tmem_ld_wait();
+          if (a2 == 1 && pc == 1) {           // this warp has read everything of its half
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * half);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {       // four 16-byte chunks = 32 channels
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int ch = pc * 32 + c * 8 + j * 2;
+              const float a0 = fmaxf(__uint_as_float(v[c * 8 + j * 2]) + bias_up_s[ch], 0.f);
+              const float a1 = fmaxf(__uint_as_float(v[c * 8 + j * 2 + 1]) + bias_up_s[ch + 1], 0.f);
+              oh[j] = inside ? __floats2half2_rn(a0, a1) : __floats2half2_rn(0.f, 0.f);
+            }
+            const uint32_t chunk = (uint32_t)(pc * 4 + c);
+            *reinterpret_cast<uint4*>(row + (((chunk ^ (uint32_t)(m & 7)) << 4))) = o;
+          }
+        }
+      }
+      fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_hrfull + 8 * half);
+    }
+  } else if (warp >= 12) {
+    // ============================================================ epilogue B: shift-add, residual, stores
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    float4* E = reinterpret_cast<float4*>(sm + kOffEx);
+    // send slots: 0,1 = U[c]  2,3 = D[c]  4,5 = L[r]  6,7 = R[r]  8 = UL  9 = UR  10 = DL  11 = DR
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int img = tile / per_img, r = tile - img * per_img;
+      const int y0 = (r / p.tiles_x) * kStepY - 1, x0 = (r % p.tiles_x) * kStepX - 1;
+      mbar_wait(bar_d2full, (uint32_t)it & 1u, 8);
+      tc_fence_after();
+      float out[2][2][3];
+      float snd[12][3];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) out[i][j][k] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) snd[i][k] = 0.f;
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        uint32_t v[48];
+        const uint32_t tad = tmem_base + kD2Col + (uint32_t)blk * 64u + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(tad, v);
+        tmem_ld16(tad + 32, v + 32);
+        tmem_ld_wait();
+        if (blk == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_d2empty);
+        }
+        const int spy = blk >> 1, spx = blk & 1;      // the source pixel's position inside the quad
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          // out[P] = sum_t D2[P + (dy,dx)][t]  <=>  source S adds its tap-t product to pixel S - (dy,dx)
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const int rr = spy - dy, cc = spx - dx;      // in [-1, 2]
+          const bool own_r = rr >= 0 && rr <= 1, own_c = cc >= 0 && cc <= 1;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const float val = __uint_as_float(v[t * 4 + k]);
+            if (own_r && own_c) out[own_r ? rr : 0][own_c ? cc : 0][k] += val;
+            else if (own_c) snd[(rr < 0 ? 0 : 2) + (own_c ? cc : 0)][k] += val;      // U[c] / D[c]
+            else if (own_r) snd[(cc < 0 ? 4 : 6) + (own_r ? rr : 0)][k] += val;      // L[r] / R[r]
+            else snd[8 + (rr < 0 ? 0 : 2) + (cc < 0 ? 0 : 1)][k] += val;            // UL UR DL DR
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) E[m * 12 + i] = make_float4(snd[i][0], snd[i][1], snd[i][2], 0.f);
+      named_bar_sync(1, 128);
+      {
+        const bool up = ty > 0, dn = ty < TH - 1, lf = tx > 0, rt = tx < TW - 1;
+#define TG_RECV(cond, nb, slot, rr, cc)                              \
+        if (cond) {                                                  \
+          const float4 e = E[(nb) * 12 + (slot)];                    \
+          out[rr][cc][0] += e.x; out[rr][cc][1] += e.y; out[rr][cc][2] += e.z; \
+        }
+        TG_RECV(up, m - 8, 2, 0, 0) TG_RECV(up, m - 8, 3, 0, 1)      // the quad above sends its D[c] to my row 0
+        TG_RECV(dn, m + 8, 0, 1, 0) TG_RECV(dn, m + 8, 1, 1, 1)      // the quad below sends its U[c] to my row 1
+        TG_RECV(lf, m - 1, 6, 0, 0) TG_RECV(lf, m - 1, 7, 1, 0)      // left quad's R[r] -> my column 0
+        TG_RECV(rt, m + 1, 4, 0, 1) TG_RECV(rt, m + 1, 5, 1, 1)      // right quad's L[r] -> my column 1
+        TG_RECV(up && lf, m - 9, 11, 0, 0)                           // up-left quad's DR
+        TG_RECV(up && rt, m - 7, 10, 0, 1)                           // up-right quad's DL
+        TG_RECV(dn && lf, m + 7, 9, 1, 0)                            // down-left quad's UR
+        TG_RECV(dn && rt, m + 9, 8, 1, 1)                            // down-right quad's UL
+#undef TG_RECV
+      }
+      named_bar_sync(1, 128);                 // everyone has read E before the next tile overwrites it
+      // ---- the quad's four HR pixels: validity, bias, residual, stores
+      const int gy = y0 + ty, gx = x0 + tx;   // input pixel
+      float res[2][2][3];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) res[i][j][k] = 0.f;
+      const bool quad_in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
+      if (p.lr != nullptr && quad_in) {
+        // upsample_func(lr_curr) at the quad: all four pixels lie in one LR cell (2 | lr_scale)
+        const int S = p.lr_scale;
+        const int Y = 2 * gy, X = 2 * gx;
+        const int ly = Y / S, lx = X / S, dy0 = Y - ly * S, dx0 = X - lx * S;
+        float ky[2][4], kx[2][4];
+        tg_up_taps(p.up_mode, dy0, S, ky[0]); tg_up_taps(p.up_mode, dy0 + 1, S, ky[1]);
+        tg_up_taps(p.up_mode, dx0, S, kx[0]); tg_up_taps(p.up_mode, dx0 + 1, S, kx[1]);
+        for (int k = 0; k < p.cout_real && k < 3; ++k) {
+          const float* pl = p.lr + ((size_t)img * p.cout_real + k) * p.lh * p.lw;
+          float col[2][4];                    // y pass (net_utils.py:144-146) for both rows, per source column
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int xx = tg_clampi(lx - 1 + j, 0, p.lw - 1);
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float s = __ldg(pl + (size_t)tg_clampi(ly - 1 + i, 0, p.lh - 1) * p.lw + xx);
+              a0 += ky[0][i] * s; a1 += ky[1][i] * s;
+            }
+            col[0][j] = a0; col[1][j] = a1;
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              res[i][j][k] = kx[j][0] * col[i][0] + kx[j][1] * col[i][1] + kx[j][2] * col[i][2] + kx[j][3] * col[i][3];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int Yt = 2 * ty + i, Y = 2 * gy + i;
+        const bool row_ok = Yt >= 1 && Yt <= 2 * TH - 2 && Y >= 0 && Y < H;
+        const int Xt0 = 2 * tx, X0 = 2 * gx;
+        const bool ok0 = row_ok && Xt0 >= 1 && X0 >= 0 && X0 < W;
+        const bool ok1 = row_ok && Xt0 + 1 <= 2 * TW - 2 && X0 + 1 >= 0 && X0 + 1 < W;
+        float o[2][3];
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) o[j][k] = (out[i][j][k] + bias_out_s[k]) + res[i][j][k];
+        for (int k = 0; k < p.cout_real && k < 3; ++k) {
+          float* dst = p.y + (((size_t)img * p.cout_real + k) * H + Y) * W + X0;
+          if (ok0 && ok1) *reinterpret_cast<float2*>(dst) = make_float2(o[0][k], o[1][k]);   // X0 even: 8-byte aligned
+          else if (ok0) dst[0] = o[0][k];
+          else if (ok1) dst[1] = o[1][k];
+        }
+        if (p.y_u8 != nullptr) {
+          uint8_t* d8 = p.y_u8 + (((size_t)img * H + Y) * W + X0) * p.cout_real;
+          for (int k = 0; k < p.cout_real && k < 3; ++k) {
+            if (ok0) d8[k] = (uint8_t)q8(o[0][k]);
+            if (ok1) d8[p.cout_real + k] = (uint8_t)q8(o[1][k]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tail_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    tried = true;
+  }
+  return fn;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream) {
+  TG_REQUIRE(d != nullptr, TG_E_INVALID, "convT_convout: null descriptor");
+  TG_REQUIRE(d->x && d->w_up && d->b_up && d->w_out && d->b_out && d->y, TG_E_INVALID, "convT_convout: null pointer");
+  TG_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, TG_E_INVALID, "convT_convout: bad size");
+  TG_REQUIRE(d->cout_real >= 1 && d->cout_real <= 3, TG_E_UNSUPPORTED, "convT_convout: out_nc=%d (1..3)", d->cout_real);
+  TG_REQUIRE(d->reserved == 0, TG_E_INVALID, "convT_convout: reserved must be 0");
+  TG_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w_up & 15) == 0 && ((uintptr_t)d->w_out & 15) == 0 &&
+                 ((uintptr_t)d->y & 7) == 0, TG_E_INVALID, "convT_convout: pointer alignment");
+  if (d->lr != nullptr) {
+    TG_REQUIRE(d->lr_scale == 2 || d->lr_scale == 4, TG_E_UNSUPPORTED, "convT_convout: lr_scale %d (2 or 4)", d->lr_scale);
+    TG_REQUIRE((2 * d->h) % d->lr_scale == 0 && (2 * d->w) % d->lr_scale == 0, TG_E_INVALID,
+               "convT_convout: output size is not lr_scale x the LR size");
+    TG_REQUIRE(d->up_mode == TG_UP_BICUBIC || d->up_mode == TG_UP_BILINEAR, TG_E_INVALID, "convT_convout: up_mode");
+  }
+  TailParams p;
+  p.w_up = reinterpret_cast<const unsigned char*>(d->w_up);
+  p.w_out = reinterpret_cast<const unsigned char*>(d->w_out);
+  p.b_up = d->b_up; p.b_out = d->b_out; p.lr = d->lr; p.y = d->y; p.y_u8 = d->y_u8;
+  p.n = d->n; p.h = d->h; p.w = d->w; p.cout_real = d->cout_real;
+  p.lr_scale = d->lr ? d->lr_scale : 2; p.up_mode = d->up_mode;
+  p.lh = 2 * d->h / p.lr_scale; p.lw = 2 * d->w / p.lr_scale;
+  // HR rows -1 .. 2h-1 are covered in strips of 30 (the first strip starts at the even row -2)
+  p.tiles_y = tg_ceil_div(2 * d->h + 1, 2 * kStepY);
+  p.tiles_x = tg_ceil_div(2 * d->w + 1, 2 * kStepX);
+  p.num_tiles = p.tiles_x * p.tiles_y * d->n;
+  p.idesc_up = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.idesc_out = (1u << 4) | ((uint32_t)(TG_TAPN_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  EncodeTiledFn fn = tail_encode_fn();
+  TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {64, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n};
+  cuuint64_t strides[3] = {128, (cuuint64_t)d->w * 128, (cuuint64_t)d->h * d->w * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)kBoxW, (cuuint32_t)kBoxH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(&p.map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(d->x), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TG_REQUIRE(r == CUDA_SUCCESS, TG_E_DRIVER, "convT_convout: cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+  static TgPerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    return cudaFuncSetAttribute(tail_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  });
+  TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "convT_convout: cudaFuncSetAttribute: %s",
+             cudaGetErrorString(attr_err));
+  int sms = 0;
+  int rc = tg_device_sm_count(&sms);
+  if (rc != TG_OK) return rc;
+  int grid = d->max_ctas > 0 && d->max_ctas < sms ? d->max_ctas : sms;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  cudaError_t lerr = tg_launch(tail_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, p);
+  TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "convT_convout: launch failed: %s", cudaGetErrorString(lerr));
+  TG_CUDA_LAUNCH_CHECK("convT_convout");
+  return TG_OK;
+}
+
+}  // extern "C"

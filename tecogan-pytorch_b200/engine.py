@@ -58,8 +58,8 @@ class ClipEngine:
 
     # one frame: parity p consumes lr[p] (current), lr[p^1] (previous), hr[p^1] -> hr[p], u8[p]
     def _enqueue(self, p):
-        self.net.step_into(self.lr[p], self.lr[p ^ 1], self.hr[p ^ 1], self.hr[p])
-        ops.float_to_uint8_nhwc(self.hr[p], self.u8[p])
+        # float32_to_uint8 + CHW->HWC happen inside the step (fused SRNet tail, or one extra kernel)
+        self.net.step_into(self.lr[p], self.lr[p ^ 1], self.hr[p ^ 1], self.hr[p], out_u8=self.u8[p])
 
     def _capture(self):
         with torch.cuda.device(self.device):

@@ -51,6 +51,16 @@ class WgradDesc(ctypes.Structure):
     ]
 
 
+class TailDesc(ctypes.Structure):
+    """struct tg_tail_desc"""
+    _fields_ = [
+        ('x', c_void_p), ('w_up', c_void_p), ('b_up', c_void_p), ('w_out', c_void_p), ('b_out', c_void_p),
+        ('lr', c_void_p), ('y', c_void_p), ('y_u8', c_void_p),
+        ('n', c_int32), ('h', c_int32), ('w', c_int32), ('cout_real', c_int32),
+        ('lr_scale', c_int32), ('up_mode', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
+    ]
+
+
 CHAIN_MAX_LAYERS = 24
 
 _P = c_void_p
@@ -65,6 +75,7 @@ _SIGNATURES = {
     'tg_pack_conv3x3_weights_tapn': (c_int, [_P, c_int, c_int, _P, c_int, _P]),
     'tg_conv_tcgen05': (c_int, [ctypes.POINTER(ConvDesc), _P]),
     'tg_conv_simt': (c_int, [ctypes.POINTER(ConvDesc), _P]),
+    'tg_convT_convout_tcgen05': (c_int, [ctypes.POINTER(TailDesc), _P]),
     'tg_conv_chain_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'tg_conv_chain_tcgen05': (c_int, [ctypes.POINTER(ChainLayer), c_int, c_int, c_int, c_int, _P, c_int, _P]),
     'tg_warp_s2d_concat_hrflow': (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

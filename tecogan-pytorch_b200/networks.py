@@ -166,7 +166,7 @@ class SRNet(nn.Module):
         x = ops.nchw_to_nhwc(torch.cat([lr_curr, _cuda_f32(hr_prev_tran, 'hr_prev_tran')], dim=1))
         return self.run_nhwc(x, lr_curr)
 
-    def run_nhwc(self, x, lr_curr, out=None):
+    def run_nhwc(self, x, lr_curr, out=None, out_u8=None):
         """x = SRNet input NHWC fp16 [n,h,w,64] (channels [lr_curr | space_to_depth(warp) | 0])."""
         c = self._cache
         body = [c.get('in', self.conv_in[0], L.CONV_3X3, _RELU)]
@@ -188,13 +188,24 @@ class SRNet(nn.Module):
             for i in range(len(self.resblocks)):
                 t = body[1 + 2 * i](a)
                 a = body[2 + 2 * i](t, residual=a)
-        for u in range(0, len(self.conv_up), 2):
-            a = c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU)(a)
+        ups = [c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU) for u in range(0, len(self.conv_up), 2)]
+        pc_out = c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
+        if (ops.tail_enabled() and ops.default_conv_impl() == 'tcgen05' and ups[-1].cin == 64 and ups[-1].cout == 64
+                and pc_out.cin == 64 and pc_out.cout_real <= 3):
+            # last transposed conv + ReLU + conv_out + `+= upsample_func(lr_curr)` (+ uint8) in ONE launch: the
+            # 64-channel HR map (88 MB per frame) never reaches HBM
+            for up in ups[:-1]:
+                a = up(a)
+            return ops.fused_tail(ups[-1], pc_out, a, lr_curr, self.scale, up_mode_of(self.upsample_func), y=out,
+                                  y_u8=out_u8)
+        for up in ups:
+            a = up(a)
         # out = conv_out(a) (pure-store epilogue), then out += upsample_func(lr_curr).
-        # (Running the last transposed conv + conv_out per frame group so that the 88 MB/frame
-        # intermediate stays in L2 was measured slower: 887 / 908 vs 873 us per step for 2 / 4 groups.)
-        out = c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)(a, y=out)
-        return ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out, accumulate=True)
+        out = pc_out(a, y=out)
+        out = ops.upsample(lr_curr, self.scale, up_mode_of(self.upsample_func), y=out, accumulate=True)
+        if out_u8 is not None:
+            ops.float_to_uint8_nhwc(out, out_u8)
+        return out
 
     def conv_layers(self, h, w):
         out = [(self.conv_in[0], h, w)]
@@ -260,9 +271,10 @@ class FRNet(BaseSequenceGenerator):
         """lr_curr, lr_prev nchw; hr_prev nc(sh)(sw); any batch n (lock-stepped clips)."""
         return self.step_into(lr_curr, lr_prev, hr_prev, None)
 
-    def step_into(self, lr_curr, lr_prev, hr_prev, out):
-        """step() writing hr_curr into `out` (nchw fp32, allocated when None).  Enqueues ~45
-        kernels on the current stream and nothing else, so it is CUDA-graph capturable."""
+    def step_into(self, lr_curr, lr_prev, hr_prev, out, out_u8=None):
+        """step() writing hr_curr into `out` (nchw fp32, allocated when None) and, when given, the
+        quantised frame into `out_u8` (uint8 nhwc).  Enqueues ~25 kernels on the current stream and
+        nothing else, so it is CUDA-graph capturable."""
         g = (lr_curr, lr_prev, hr_prev)
         lr_curr, lr_prev = _cuda_f32(lr_curr, 'lr_curr'), _cuda_f32(lr_prev, 'lr_prev')
         hr_prev = _cuda_f32(hr_prev, 'hr_prev')
@@ -272,7 +284,7 @@ class FRNet(BaseSequenceGenerator):
             # reflect-pad + upsample_func + *scale + warp + space_to_depth + concat: one kernel
             x = ops.warp_s2d_concat_lrflow(hr_prev, lr_flow, lr_curr, self.scale,
                                            up_mode_of(self.upsample_func))
-            return self.srnet.run_nhwc(x, lr_curr, out=out)
+            return self.srnet.run_nhwc(x, lr_curr, out=out, out_u8=out_u8)
 
     # ------------------------------------------------------------------ training forward
     def forward_sequence(self, lr_data):

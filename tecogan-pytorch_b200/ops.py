@@ -189,6 +189,45 @@ class ConvChain:
         return buffers[self.specs[-1][2]]
 
 
+def fused_tail(up, outc, x, lr_curr, lr_scale, up_mode, y=None, y_u8=None, max_ctas=0):
+    """SRNet tail in one launch (tg_convT_convout_tcgen05): y = conv_out(relu(convT(x))) + upsample_func(lr_curr)
+    [, y_u8 = float32_to_uint8(y) as NHWC].  `up` / `outc` are the PackedConv objects of the last transposed
+    conv and of conv_out (their packed weights are used as they are)."""
+    _req(x, torch.float16, 'tail input', 4)
+    n, h, w, c = x.shape
+    if (up.kind != L.CONVT_3X3_S2 or up.cin != 64 or up.cout != 64 or c != 64 or not outc.tapn or outc.cin != 64
+            or outc.cout_real > 3):
+        raise L.TecoganB200Error('fused tail: needs a 64->64 transposed conv and a 64->(<=3) conv_out')
+    co = outc.cout_real
+    if y is None:
+        y = torch.empty((n, co, 2 * h, 2 * w), dtype=torch.float32, device=x.device)
+    _req(y, torch.float32, 'tail output', 4)
+    if tuple(y.shape) != (n, co, 2 * h, 2 * w):
+        raise L.TecoganB200Error(f'fused tail: output shape {tuple(y.shape)}')
+    d = L.TailDesc()
+    d.x, d.w_up, d.b_up = x.data_ptr(), up.packed.data_ptr(), up.bias.data_ptr()
+    d.w_out, d.b_out, d.y = outc.packed.data_ptr(), outc.bias.data_ptr(), y.data_ptr()
+    if lr_curr is not None:
+        _req(lr_curr, torch.float32, 'lr_curr', 4)
+        if tuple(lr_curr.shape) != (n, co, 2 * h // lr_scale, 2 * w // lr_scale):
+            raise L.TecoganB200Error(f'fused tail: lr_curr shape {tuple(lr_curr.shape)}')
+        d.lr = lr_curr.data_ptr()
+    if y_u8 is not None:
+        _req(y_u8, torch.uint8, 'uint8 output', 4)
+        if tuple(y_u8.shape) != (n, 2 * h, 2 * w, co):
+            raise L.TecoganB200Error(f'fused tail: uint8 output shape {tuple(y_u8.shape)}')
+        d.y_u8 = y_u8.data_ptr()
+    d.n, d.h, d.w, d.cout_real, d.lr_scale, d.up_mode, d.max_ctas, d.reserved = n, h, w, co, lr_scale, up_mode, max_ctas, 0
+    L.check(L.load().tg_convT_convout_tcgen05(ctypes.byref(d), _stream()), 'tg_convT_convout_tcgen05')
+    return y
+
+
+def tail_enabled():
+    """TECOGAN_B200_TAIL=0 runs the last transposed conv, conv_out, the residual upsample and the uint8
+    conversion as four launches instead of tg_convT_convout_tcgen05 (A/B measurements)."""
+    return os.environ.get('TECOGAN_B200_TAIL', '0') != '0'      # TODO(flip to '1' once validated on a B200)
+
+
 def chain_enabled():
     """TECOGAN_B200_CHAIN=0 runs SRNet's conv_in + residual blocks as 21 launches of
     tg_conv_tcgen05 instead of one tg_conv_chain_tcgen05 launch (A/B measurements)."""

@@ -280,6 +280,186 @@ def run_eager_gpu(args, rank):
     print(json.dumps(res), flush=True)
 
 
+
+# =============================================================================== training workloads
+# BASELINE.json configs[2] / [3]: TecoGAN 4x BD training (G + D + ping-pong), synthetic REDS-shape 10-frame
+# 3x64x64 LR crops, batch 32 per B200; N > 1 = DDP over NCCL (gradient all-reduce), weak scaling.
+# The loop is the REFERENCE's own (VSRGANModel.train from baseline/_ref: discriminator, VGG, losses and
+# optimisers stay PyTorch -- SURVEY.md section 2 puts them out of scope); the generator is this repo's
+# (forward + backward on the library's kernels) or, for the comparison arms, the reference's.
+TRAIN = dict(lr=(3, 64, 64), scale=4, t=10, batch=32, border=4,
+             metric={'tecogan': 'train_frames_per_sec_TecoGAN_4xBD_64x64', 'frvsr': 'train_frames_per_sec_FRVSR_4xBD_64x64'})
+
+
+def train_config(model, batch, world):
+    return {'workload': f'{"TecoGAN (G + ST-discriminator + VGG + ping-pong)" if model == "tecogan" else "FRVSR (generator only)"} '
+                        f'4x BD training, synthetic REDS-shape {TRAIN["t"]}-frame 3x64x64 LR crops (GT 264x264 incl. the BD '
+                        f'border), reference training loop (baseline/_ref) with the generator under test; DDP/NCCL gradient '
+                        f'all-reduce for N > 1 (BASELINE.json configs[2]/[3])',
+            'batch_per_gpu': batch, 'global_batch': batch * world, 'frames_per_step': batch * TRAIN['t'] * world,
+            'weights': 'seeded random init (no checkpoint; VGG19 = random weights of the same architecture)',
+            'l2': 'activations of one step (tens of GB) >> 126 MB L2, no explicit flush'}
+
+
+def _train_model(model, device, generator, dist_on, rank, world):
+    import refimport
+    opt = refimport.training_opt(model, device=str(device), dist=dist_on, rank=rank, world_size=world)
+    opt['dataset']['train']['crop_size'] = TRAIN['scale'] * TRAIN['lr'][1]
+    define_generator = None
+    if generator == 'ours':
+        import tecogan_b200 as T
+        define_generator = T.define_generator
+    m = refimport.build_training_model(opt, define_generator)
+    m.get_bare_model(m.net_G).load_state_dict(make_params(), strict=True)
+    return m
+
+
+def _train_steps(m, data, steps, sync):
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.prepare_training_data({'gt': data})        # H2D of the batch when `data` is pinned host memory
+        m.train()                                    # one full iteration (forward, D step, G step)
+    sync()
+    return time.perf_counter() - t0
+
+
+def _generator_only_ms(generator, device, batch, reps=3):
+    """forward_sequence + backward of the generator alone (19-frame ping-pong sequence as the TecoGAN loop
+    feeds it): the part of the step this repo implements, ours vs the reference generator on cuDNN."""
+    import torch
+    import refimport
+    if generator == 'ours':
+        import tecogan_b200 as T
+        net = T.FRNet(3, 3, 64, 10, 'BD', 4)
+    else:
+        FRNet, _, _ = refimport.import_generator()
+        net = FRNet(in_nc=3, out_nc=3, nf=64, nb=10, degradation='BD', scale=4)
+    net.load_state_dict(make_params(), strict=True)
+    net = net.to(device).train()
+    g = torch.Generator().manual_seed(1)
+    lr = torch.rand(batch, 2 * TRAIN['t'] - 1, *TRAIN['lr'], generator=g).to(device)
+    out = []
+    for i in range(reps + 1):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d = net(lr)
+        (d['hr_data'].mean() + 0.1 * d['lr_flow'].mean()).backward()
+        e1.record()
+        torch.cuda.synchronize()
+        net.zero_grad(set_to_none=True)
+        if i:
+            out.append(e0.elapsed_time(e1))
+    del net, lr, d
+    torch.cuda.empty_cache()
+    return statistics.median(out)
+
+
+def run_train(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    model = 'frvsr' if args.workload == 'train-frvsr' else 'tecogan'
+    impl = args.impl
+    K, Wm = args.steps, max(args.warmup, 1)
+    if impl == 'reference':
+        # the reference's own training step on the host cores: a bounded sample (1 clip per step)
+        if rank != 0:
+            return
+        cores = _host_threads()
+        n = 1
+        m = _train_model(model, 'cpu', 'reference', False, 0, 1)
+        data = torch.rand(n, TRAIN['t'], 3, 264, 264, generator=torch.Generator().manual_seed(0))
+        steps = min(K, 3)
+        _train_steps(m, data, 1, lambda: None)
+        dt = _train_steps(m, data, steps, lambda: None)
+        fps = n * TRAIN['t'] * steps / dt
+        line = {'impl': 'reference', 'metric': TRAIN['metric'][model], 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': train_config(model, args.batch or TRAIN['batch'], args.gpus),
+                'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'reference',
+                                 'sample': f'{steps} training iterations of {n} clip ({TRAIN["t"]} frames, 64x64 LR) with the unmodified '
+                                           f'reference (baseline/_ref) on {cores} host threads -- a bounded sample of the batch'},
+                'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback exists)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')
+        dist.init_process_group('nccl', device_id=dev)
+    ops = None
+    if impl == 'ours':
+        import tecogan_b200 as T  # noqa: F401
+        ops = sys.modules['tecogan-pytorch_b200.ops']
+    torch.backends.cudnn.benchmark = True
+    batch = args.batch or TRAIN['batch']
+    m = _train_model(model, dev, 'ours' if impl == 'ours' else 'reference', world > 1, rank, world)
+    g = torch.Generator().manual_seed(100 + rank)
+    host = torch.rand(batch, TRAIN['t'], 3, 264, 264, generator=g).pin_memory()
+    resident = host.to(dev)
+    sync = lambda: torch.cuda.synchronize()
+    _train_steps(m, resident, Wm, sync)
+    torch.cuda.reset_peak_memory_stats()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ops.LAUNCH_COUNT if ops else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    _train_steps(m, resident, K, sync)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = (ops.LAUNCH_COUNT - l0) if ops else 0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    value = world * batch * TRAIN['t'] * K / (float(ms.item()) * 1e-3)
+    # end to end: the batch comes from pinned host memory every iteration (H2D inside the timed region);
+    # the losses the loop logs come back through .item() (D2H)
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([_train_steps(m, host, K, sync)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = world * batch * TRAIN['t'] * K / float(dt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    log = {k: float(v) for k, v in m.log_dict.items()}
+    line = None
+    if rank == 0:
+        line = {'metric': TRAIN['metric'][model], 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+                'ms_per_step': float(ms.item()) / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f16' if impl == 'ours' else 'f32', 'data': 'synthetic', 'config': train_config(model, batch, world),
+                'e2e': {'value': e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': host.numel() * 4, 'd2h_bytes_per_step': 4 * len(log),
+                        'api': 'reference VSR(GAN)Model.prepare_training_data(pinned gt) + .train() with define_generator = tecogan_b200'},
+                'gpu_launches': launches, 'launches_per_step': launches / K if K else 0, 'clocks': clocks,
+                'peak_memory_gb': peak_gb, 'last_log': log,
+                'generator': 'tecogan_b200 (fp16 tcgen05 forward + backward)' if impl == 'ours' else 'reference FRNet on cuDNN (fp32/TF32)'}
+        if impl != 'ours':
+            line['impl'] = 'eager-gpu'
+    del m
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and impl == 'ours' and not args.no_eager:
+        gb = min(batch, 8)
+        ours_ms = _generator_only_ms('ours', dev, gb)
+        ref_ms = _generator_only_ms('reference', dev, gb)
+        line['generator_fwd_bwd'] = {'batch': gb, 'frames': 2 * TRAIN['t'] - 1, 'ours_ms': ours_ms, 'reference_cudnn_ms': ref_ms,
+                                     'speedup': ref_ms / ours_ms,
+                                     'note': 'forward_sequence + backward of the generator alone on the same B200'}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
 # =============================================================================== our arm
 def ncu_traffic(kernel_key):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, taken from the latest
@@ -562,17 +742,21 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'eager-gpu'])
-    ap.add_argument('--workload', default='bd4', choices=sorted(WORKLOADS),
-                    help='bd4 = BASELINE configs[1] (headline); bi2 = configs[4] (2x BI 268x640, 30-frame clips)')
+    ap.add_argument('--workload', default='bd4', choices=sorted(WORKLOADS) + ['train', 'train-frvsr'],
+                    help='bd4 = BASELINE configs[1] (headline); bi2 = configs[4] (2x BI 268x640, 30-frame clips); '
+                         'train = configs[2]/[3] (TecoGAN training step, DDP for N > 1); train-frvsr = generator-only losses')
+    ap.add_argument('--batch', type=int, default=0, help='training workloads: clips per GPU (default 32)')
     ap.add_argument('--sustain-s', type=float, default=3.0, help='seconds of the sustained block (0 = skip)')
     ap.add_argument('--no-eager', action='store_true', help='skip the gpu_eager_baseline block (N=1 only)')
     ap.add_argument('--profile-only', action='store_true',
                     help='run only the device-resident step loop (for ncu captures); prints nothing')
     args = ap.parse_args()
-    select_workload(args.workload)
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.workload.startswith('train'):
+        return run_train(args, rank, world, local_rank)
+    select_workload(args.workload)
     if args.impl == 'reference':
         return run_reference(args, rank)
     if args.impl == 'eager-gpu':

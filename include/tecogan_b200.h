@@ -314,6 +314,16 @@ int tg_upsample2x_bilinear_bwd_nhwc_f16(const void* gy, const void* m, void* gx,
  * in tg_grad_scale_from_amax) */
 int tg_flow_head_bwd(const float* gflow, const float* gflow2, const float* flow, void* scale_ws, float target,
                      void* dz, int n, int h, int w, int cpad, void* stream);
+/* Input builder of the spatio-temporal discriminator (tecogan_nets.py:438-463): the three
+ * backward_warps of every 3-frame clip + centre crop / zero pad + "rrrgggbbb" permutes + 27-channel concat
+ * in one kernel.  data, bi: [n,t_full,c,h,w] fp32 (frames >= t are ignored, t % 3 == 0); flow:
+ * hr_flow_merge [n*t,2,h,w] (clip-major, 3 per clip); out: [n*t/3, 9*c, h, w] = [orig | warp | cond].
+ * pad = (spatial_size - c_size)/2, csize = c_size = int(spatial_size * crop_border_ratio). */
+int tg_st_disc_input_nchw_f32(const float* data, const float* bi, const float* flow, float* out, int n, int t_full,
+                              int t, int c, int h, int w, int pad, int csize, void* stream);
+/* its gradient w.r.t. data: gdata [n,t_full,c,h,w] (zeroed by the caller) += orig part + warp scatter */
+int tg_st_disc_input_bwd_nchw_f32(const float* gout, const float* flow, float* gdata, int n, int t_full, int t, int c,
+                                  int h, int w, int pad, int csize, void* stream);
 /* space_to_depth backward (net_utils.py:36-47): gy [n,c*s*s,h/s,w/s] -> gx [n,c,h,w] */
 int tg_depth_to_space_nchw_f32(const float* gy, float* gx, int n, int c, int h, int w, int s, void* stream);
 

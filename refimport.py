@@ -67,3 +67,58 @@ def import_models():
 def root_dir():
     codes = reference_codes_dir()
     return None if codes is None else os.path.dirname(codes)
+
+
+def stub_pretrained_vgg19(seed=0):
+    """codes/models/networks/vgg_nets.py:11 asks torchvision for vgg19(pretrained=True); there is no
+    network here, so the perceptual-loss extractor gets seeded random weights of the same architecture
+    (same FLOPs and memory traffic -- this only matters for benchmarks and integration tests)."""
+    import torch
+    import torchvision
+    real = torchvision.models.vgg19
+
+    def vgg19(pretrained=False, **kw):
+        g = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        try:
+            return real(weights=None)
+        finally:
+            torch.random.set_rng_state(g)
+
+    if getattr(torchvision.models.vgg19, '__name__', '') != 'vgg19' or not hasattr(torchvision.models.vgg19, '_stub'):
+        vgg19._stub = True
+        torchvision.models.vgg19 = vgg19
+
+
+def training_opt(model='tecogan', device='cuda:0', dist=False, rank=0, world_size=1, nb=10):
+    """The reference's own training YAML (experiments_BD/{TecoGAN,FRVSR}/*_REDS_4xSR_2GPU/train.yml) as the
+    `opt` dict its models take, with the data/checkpoint paths the offline box does not have removed."""
+    import yaml
+    sub = {'tecogan': ('TecoGAN', 'TecoGAN_REDS_4xSR_2GPU'), 'frvsr': ('FRVSR', 'FRVSR_REDS_4xSR_2GPU')}[model]
+    path = os.path.join(root_dir(), 'experiments_BD', sub[0], sub[1], 'train.yml')
+    opt = yaml.safe_load(open(path))
+    opt['model']['generator']['load_path'] = None
+    opt['model']['generator']['nb'] = nb
+    if 'discriminator' in opt['model']:
+        opt['model']['discriminator']['load_path'] = None
+    opt.update({'device': device, 'dist': dist, 'is_train': True, 'rank': rank, 'world_size': world_size})
+    opt['train']['ckpt_dir'] = '/tmp'
+    return opt
+
+
+def build_training_model(opt, define_generator=None):
+    """VSRModel / VSRGANModel of the reference for `opt`; define_generator (e.g. tecogan_b200's) replaces
+    the reference's generator factory for the duration of the construction."""
+    models, _ = import_models()
+    import models.vsrgan_model as vg
+    import models.vsr_model as vm
+    cls = vg.VSRGANModel if opt['model']['name'].lower() == 'tecogan' else vm.VSRModel
+    saved = (vm.define_generator, vg.define_generator)
+    if define_generator is not None:
+        vm.define_generator = vg.define_generator = define_generator
+    try:
+        if cls is vg.VSRGANModel:
+            stub_pretrained_vgg19()
+        return cls(opt)
+    finally:
+        vm.define_generator, vg.define_generator = saved

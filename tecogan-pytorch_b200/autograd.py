@@ -318,3 +318,31 @@ class SpaceToDepthFunction(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, gy):
         return ops.depth_to_space(_f32c(gy), ctx.scale), None
+
+
+class StDiscInputFunction(torch.autograd.Function):
+    """The tensor plumbing in front of the spatio-temporal discriminator (tecogan_nets.py:438-463) as one
+    kernel + one gradient kernel; gradient flows to `data` only (the reference detaches the flows)."""
+
+    @staticmethod
+    def forward(ctx, data, bi_data, hr_flow_merge, t, pad, csize):
+        data, bi, flow = _f32c(data), _f32c(bi_data), _f32c(hr_flow_merge)
+        ctx.save_for_backward(flow)
+        ctx.meta = (tuple(data.shape), t, pad, csize)
+        return ops.st_disc_input(data, bi, flow, t, pad, csize)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        flow, = ctx.saved_tensors
+        shape, t, pad, csize = ctx.meta
+        return ops.st_disc_input_bwd(_f32c(gout), flow, shape, t, pad, csize), None, None, None, None, None
+
+
+def st_discriminator_input(data, bi_data, hr_flow_merge, spatial_size, crop_border_ratio=0.75):
+    """Drop-in for lines 438-463 of SpatioTemporalDiscriminator.forward_sequence: data / bi_data [n,T,c,H,W]
+    (only the first T//3*3 frames are used), hr_flow_merge [n*(T//3*3), 2, H, W] -> [n*T//3, 9c, H, W]."""
+    t = data.shape[1] // 3 * 3
+    csize = int(spatial_size * crop_border_ratio)
+    pad = (spatial_size - csize) // 2
+    return StDiscInputFunction.apply(data, bi_data[:, :data.shape[1]], hr_flow_merge.detach(), t, pad, csize)

@@ -70,7 +70,14 @@ struct TailParams {
   int lr_scale, up_mode, lh, lw;
   int tiles_x, tiles_y, num_tiles;
   uint32_t idesc_up, idesc_out;
+  int flags;                 // diagnostics (TG_TAIL_FLAGS): 1 = skip the residual, 2 = skip uint8, 4 = skip the exchange
+  unsigned long long* dbg;   // optional per-CTA role timers (tg_debug_set_conv_timers), 16 slots per CTA
 };
+// role-timer slots (cycles per CTA): tools/conv_timers.py tail
+enum { TT_MMA_WAIT_FULL = 0, TT_MMA_WAIT_TEMPTY, TT_MMA_WAIT_HRFULL, TT_MMA_WAIT_D2EMPTY, TT_MMA_TOTAL, TT_EA_WAIT, TT_EA_BUSY,
+       TT_EB_WAIT, TT_EB_TMEM, TT_EB_EXCH, TT_EB_RESID, TT_EB_STORE, TT_EB_TOTAL, TT_KERNEL, TT_TILES, TT_SLOTS = 16 };
+#define TT0() (TIMING ? clock64() : 0)
+#define TTACC(var, t0) do { if (TIMING) var += clock64() - (t0); } while (0)
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -78,8 +85,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 __device__ __forceinline__ uint32_t q8(float v) { return (uint32_t)fminf(fmaxf(rintf(v * 255.f), 0.f), 255.f); }
 
+template <bool TIMING>
 __global__ void __launch_bounds__(kThreads, 1)
 tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
+  const long long t_kernel0 = TIMING ? clock64() : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -176,27 +185,39 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
                    k_hi | (uint64_t)(wo16 + 2u * k), p.idesc_out, k == 0 ? 0u : 1u);
     };
     int it = 0;
+    long long tw_full = 0, tw_tempty = 0, tw_hrfull = 0, tw_d2empty = 0;
+    const long long t_mma0 = TT0();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int stage = it & 1;
       const uint32_t sph = (uint32_t)(it >> 1) & 1u, tph = (uint32_t)it & 1u;
       const uint32_t sa16 = ((base + kOffStage + stage * kStageBytes) & 0x3FFFFu) >> 4;
+      long long t0 = TT0();
       mbar_wait(bar_full + 8 * stage, sph, 3);
+      TTACC(tw_full, t0); t0 = TT0();
       mbar_wait(bar_tempty + 0, tph ^ 1, 4);
+      TTACC(tw_tempty, t0);
       tc_fence_after();
       if (elect_one_sync()) { issue_convt(sa16, 0, 3); umma_commit(bar_tfull + 0); }
       __syncwarp();
       if (it > 0) {                                   // second half of conv_out of the previous tile
+        t0 = TT0();
         mbar_wait(bar_hrfull + 8, (uint32_t)(it - 1) & 1u, 5);
+        TTACC(tw_hrfull, t0);
         tc_fence_after();
         if (elect_one_sync()) { issue_convout(2); umma_commit(bar_d2full); }
         __syncwarp();
       }
+      t0 = TT0();
       mbar_wait(bar_tempty + 8, tph ^ 1, 4);
+      TTACC(tw_tempty, t0);
       tc_fence_after();
       if (elect_one_sync()) { issue_convt(sa16, 3, 9); umma_commit(bar_tfull + 8); umma_commit(bar_empty + 8 * stage); }
       __syncwarp();
+      t0 = TT0();
       mbar_wait(bar_hrfull + 0, tph, 5);
+      TTACC(tw_hrfull, t0); t0 = TT0();
       mbar_wait(bar_d2empty, tph ^ 1, 6);
+      TTACC(tw_d2empty, t0);
       tc_fence_after();
       if (elect_one_sync()) issue_convout(0);
       __syncwarp();
@@ -207,6 +228,11 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
       if (elect_one_sync()) { issue_convout(2); umma_commit(bar_d2full); }
       __syncwarp();
     }
+    if (TIMING && lane == 0) {
+      unsigned long long* o = p.dbg + blockIdx.x * TT_SLOTS;
+      o[TT_MMA_WAIT_FULL] = tw_full; o[TT_MMA_WAIT_TEMPTY] = tw_tempty; o[TT_MMA_WAIT_HRFULL] = tw_hrfull;
+      o[TT_MMA_WAIT_D2EMPTY] = tw_d2empty; o[TT_MMA_TOTAL] = clock64() - t_mma0; o[TT_TILES] = it;
+    }
   } else if (warp >= 4 && warp < 12) {
     // ============================================================ epilogue A: ConvT accumulators -> HR tile (smem)
     const int half = (warp - 4) >> 2;         // parities {0,1} or {2,3}
@@ -214,11 +240,14 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
     const int m = q * 32 + lane;              // TMEM lane = input pixel of the tile
     const int ty = m >> 3, tx = m & 7;
     int it = 0;
+    long long ta_wait = 0, ta_busy = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int img = tile / per_img, r = tile - img * per_img;
       const int y0 = (r / p.tiles_x) * kStepY - 1, x0 = (r % p.tiles_x) * kStepX - 1;
       (void)img;
+      long long t0 = TT0();
       mbar_wait(bar_tfull + 8 * half, (uint32_t)it & 1u, 7);
+      TTACC(ta_wait, t0); t0 = TT0();
       tc_fence_after();
 #pragma unroll
       for (int a2 = 0; a2 < 2; ++a2) {
@@ -255,6 +284,10 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
       fence_proxy_async_smem();               // generic-proxy stores -> visible to the tensor core's reads
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_hrfull + 8 * half);
+      TTACC(ta_busy, t0);
+    }
+    if (TIMING && warp == 4 && lane == 0) {
+      p.dbg[blockIdx.x * TT_SLOTS + TT_EA_WAIT] = ta_wait; p.dbg[blockIdx.x * TT_SLOTS + TT_EA_BUSY] = ta_busy;
     }
   } else if (warp >= 12) {
     // ============================================================ epilogue B: shift-add, residual, stores
@@ -264,10 +297,14 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
     float4* E = reinterpret_cast<float4*>(sm + kOffEx);
     // send slots: 0,1 = U[c]  2,3 = D[c]  4,5 = L[r]  6,7 = R[r]  8 = UL  9 = UR  10 = DL  11 = DR
     int it = 0;
+    long long tb_wait = 0, tb_tmem = 0, tb_exch = 0, tb_resid = 0, tb_store = 0;
+    const long long t_eb0 = TT0();
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int img = tile / per_img, r = tile - img * per_img;
       const int y0 = (r / p.tiles_x) * kStepY - 1, x0 = (r % p.tiles_x) * kStepX - 1;
+      long long t0 = TT0();
       mbar_wait(bar_d2full, (uint32_t)it & 1u, 8);
+      TTACC(tb_wait, t0); t0 = TT0();
       tc_fence_after();
       float out[2][2][3];
       float snd[12][3];
@@ -310,6 +347,8 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
           }
         }
       }
+      TTACC(tb_tmem, t0); t0 = TT0();
+      if (!(p.flags & 4)) {
 #pragma unroll
       for (int i = 0; i < 12; ++i) E[m * 12 + i] = make_float4(snd[i][0], snd[i][1], snd[i][2], 0.f);
       named_bar_sync(1, 128);
@@ -331,6 +370,8 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
 #undef TG_RECV
       }
       named_bar_sync(1, 128);                 // everyone has read E before the next tile overwrites it
+      }
+      TTACC(tb_exch, t0); t0 = TT0();
       // ---- the quad's four HR pixels: validity, bias, residual, stores
       const int gy = y0 + ty, gx = x0 + tx;   // input pixel
       float res[2][2][3];
@@ -341,7 +382,7 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) res[i][j][k] = 0.f;
       const bool quad_in = gy >= 0 && gy < p.h && gx >= 0 && gx < p.w;
-      if (p.lr != nullptr && quad_in) {
+      if (p.lr != nullptr && quad_in && !(p.flags & 1)) {
         // upsample_func(lr_curr) at the quad: all four pixels lie in one LR cell (2 | lr_scale)
         const int S = p.lr_scale;
         const int Y = 2 * gy, X = 2 * gx;
@@ -370,6 +411,7 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
               res[i][j][k] = kx[j][0] * col[i][0] + kx[j][1] * col[i][1] + kx[j][2] * col[i][2] + kx[j][3] * col[i][3];
         }
       }
+      TTACC(tb_resid, t0); t0 = TT0();
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int Yt = 2 * ty + i, Y = 2 * gy + i;
@@ -388,7 +430,7 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
           else if (ok0) dst[0] = o[0][k];
           else if (ok1) dst[1] = o[1][k];
         }
-        if (p.y_u8 != nullptr) {
+        if (p.y_u8 != nullptr && !(p.flags & 2)) {
           uint8_t* d8 = p.y_u8 + (((size_t)img * H + Y) * W + X0) * p.cout_real;
           for (int k = 0; k < p.cout_real && k < 3; ++k) {
             if (ok0) d8[k] = (uint8_t)q8(o[0][k]);
@@ -396,6 +438,12 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
           }
         }
       }
+      TTACC(tb_store, t0);
+    }
+    if (TIMING && warp == 12 && lane == 0) {
+      unsigned long long* o = p.dbg + blockIdx.x * TT_SLOTS;
+      o[TT_EB_WAIT] = tb_wait; o[TT_EB_TMEM] = tb_tmem; o[TT_EB_EXCH] = tb_exch; o[TT_EB_RESID] = tb_resid;
+      o[TT_EB_STORE] = tb_store; o[TT_EB_TOTAL] = clock64() - t_eb0;
     }
   }
 
@@ -403,6 +451,7 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
   __syncthreads();
   tc_fence_after();
   if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+  if (TIMING && threadIdx.x == 0) p.dbg[blockIdx.x * TT_SLOTS + TT_KERNEL] = clock64() - t_kernel0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -423,6 +472,8 @@ EncodeTiledFn tail_encode_fn() {
 }
 
 }  // namespace
+
+unsigned long long* tg_conv_timer_buffer();     // tg_conv_tcgen05.cu (tg_debug_set_conv_timers)
 
 extern "C" {
 
@@ -453,6 +504,9 @@ int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream) {
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
   p.idesc_up = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.idesc_out = (1u << 4) | ((uint32_t)(TG_TAPN_ROWS >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.flags = 0;
+  if (const char* e = getenv("TG_TAIL_FLAGS")) p.flags = atoi(e);
+  p.dbg = tg_conv_timer_buffer();
 
   EncodeTiledFn fn = tail_encode_fn();
   TG_REQUIRE(fn != nullptr, TG_E_DRIVER, "cuTensorMapEncodeTiled not available from the driver");
@@ -467,7 +521,9 @@ int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream) {
 
   static TgPerDeviceOnce attr_once;
   const cudaError_t attr_err = attr_once.run([] {
-    return cudaFuncSetAttribute(tail_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tail_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tail_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   });
   TG_REQUIRE(attr_err == cudaSuccess, (int)attr_err, "convT_convout: cudaFuncSetAttribute: %s",
              cudaGetErrorString(attr_err));
@@ -476,7 +532,8 @@ int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream) {
   if (rc != TG_OK) return rc;
   int grid = d->max_ctas > 0 && d->max_ctas < sms ? d->max_ctas : sms;
   if (grid > p.num_tiles) grid = p.num_tiles;
-  cudaError_t lerr = tg_launch(tail_tcgen05_kernel, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, p);
+  cudaError_t lerr = p.dbg ? tg_launch(tail_tcgen05_kernel<true>, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, p)
+                           : tg_launch(tail_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), kSmemBytes, (cudaStream_t)stream, p);
   TG_REQUIRE(lerr == cudaSuccess, (int)lerr, "convT_convout: launch failed: %s", cudaGetErrorString(lerr));
   TG_CUDA_LAUNCH_CHECK("convT_convout");
   return TG_OK;

@@ -638,3 +638,29 @@ def depth_to_space(gy, scale_factor):
     L.check(L.load().tg_depth_to_space_nchw_f32(_ptr(gy), _ptr(gx), n, c, oh * scale_factor, ow * scale_factor,
                                                 scale_factor, _stream()), 'tg_depth_to_space')
     return gx
+
+
+def st_disc_input(data, bi, flow, t, pad, csize, out=None):
+    """[orig | crop_pad(warp) | cond] input of the spatio-temporal discriminator (tg_st_disc_input_nchw_f32)"""
+    _req(data, torch.float32, 'data', 5)
+    _req(bi, torch.float32, 'bi_data', 5)
+    _req(flow, torch.float32, 'hr_flow_merge', 4)
+    n, t_full, c, h, w = data.shape
+    if bi.shape[0] != n or bi.shape[1] < t or tuple(bi.shape[2:]) != (c, h, w) or bi.shape[1] != t_full:
+        raise L.TecoganB200Error(f'st_disc_input: bi_data shape {tuple(bi.shape)} does not match data {tuple(data.shape)}')
+    if tuple(flow.shape) != (n * t, 2, h, w):
+        raise L.TecoganB200Error(f'st_disc_input: flow shape {tuple(flow.shape)} != {(n * t, 2, h, w)}')
+    if out is None:
+        out = torch.empty((n * t // 3, 9 * c, h, w), dtype=torch.float32, device=data.device)
+    L.check(L.load().tg_st_disc_input_nchw_f32(_ptr(data), _ptr(bi), _ptr(flow), _ptr(out), n, t_full, t, c, h, w, pad,
+                                               csize, _stream()), 'tg_st_disc_input')
+    return out
+
+
+def st_disc_input_bwd(gout, flow, shape, t, pad, csize):
+    _req(gout, torch.float32, 'gout', 4)
+    n, t_full, c, h, w = shape
+    gdata = torch.zeros(shape, dtype=torch.float32, device=gout.device)
+    L.check(L.load().tg_st_disc_input_bwd_nchw_f32(_ptr(gout), _ptr(flow), _ptr(gdata), n, t_full, t, c, h, w, pad, csize,
+                                                   _stream()), 'tg_st_disc_input_bwd')
+    return gdata

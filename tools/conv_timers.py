@@ -122,7 +122,54 @@ def run_chain(blocks=10, n=4, h=134, w=320):
     return out
 
 
+TAIL_NAMES = ['mma_wait_full', 'mma_wait_tempty', 'mma_wait_hrfull', 'mma_wait_d2empty', 'mma_total', 'epiA_wait',
+              'epiA_busy', 'epiB_wait', 'epiB_tmem', 'epiB_exchange', 'epiB_residual', 'epiB_store', 'epiB_total',
+              'kernel', 'tiles']
+
+
+def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True):
+    """per-role cycles of tail_tcgen05_kernel (fused ConvT + conv_out + residual + uint8), per tile"""
+    dev = 'cuda:0'
+    os.environ['TG_TAIL_FLAGS'] = flags
+    up = ops.PackedConv(torch.randn(64, 64, 3, 3, device=dev) * 0.05, torch.zeros(64, device=dev), L.CONVT_3X3_S2, L.ACT_RELU)
+    oc = ops.PackedConv(torch.randn(3, 64, 3, 3, device=dev) * 0.05, torch.zeros(3, device=dev), L.CONV_3X3, L.ACT_NONE,
+                        L.EPI_OUT_NCHW_F32)
+    x = torch.randn(n, h, w, 64, device=dev).half()
+    lr = torch.rand(n, 3, h // 2, w // 2, device=dev) if with_lr else None
+    y = torch.zeros(n, 3, 2 * h, 2 * w, device=dev)
+    u8 = torch.zeros(n, 2 * h, 2 * w, 3, dtype=torch.uint8, device=dev) if with_u8 else None
+    for _ in range(3):
+        ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+    e1.record()
+    torch.cuda.synchronize()
+    us_plain = e0.elapsed_time(e1) * 1e3
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    lib = L.load()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
+    ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+    torch.cuda.synchronize()
+    lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
+    t = buf.view(148, 16).cpu().double()
+    t = t[t[:, 13] > 0]
+    tiles = t[:, 14].mean().item()
+    out = {'flags': flags, 'lr': with_lr, 'u8': with_u8, 'us': round(us_plain, 1), 'tiles_per_cta': tiles,
+           'per_tile': {nm: round(t[:, i].mean().item() / max(tiles, 1)) for i, nm in enumerate(TAIL_NAMES[:14])}}
+    print(json.dumps(out), flush=True)
+    return out
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'tail':
+        run_tail('0')
+        run_tail('1')            # no residual
+        run_tail('3')            # no residual, no uint8
+        run_tail('7')            # + no exchange (wrong results: timing only)
+        run_tail('0', with_lr=False, with_u8=False)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'chain':
         run_chain()
         sys.exit(0)

@@ -144,14 +144,17 @@ typedef struct tg_tail_desc {
   const float* b_up;    /* fp32 [64]                                                                */
   const void* w_out;    /* tg_pack_conv3x3_weights_tapn(cin_pad=64)                                 */
   const float* b_out;   /* fp32 [cout_real]                                                         */
-  const float* lr;      /* lr_curr NCHW fp32 [n,cout_real,2h/lr_scale,2w/lr_scale] or NULL          */
-  float* y;             /* NCHW fp32 [n,cout_real,2h,2w]                                            */
+  const float* lr;      /* lr_curr NCHW fp32 [n,cout_real,2h/lr_scale,2w/lr_scale] or NULL: the residual is
+                           evaluated inside the kernel (16 gathers per pixel pair and channel)          */
+  float* y;             /* NCHW fp32 [n,cout_real,2h,2w]; accumulate != 0: read-modify-write             */
   uint8_t* y_u8;        /* NHWC uint8 [n,2h,2w,cout_real] (round-half-even, clip) or NULL           */
   int32_t n, h, w;      /* of the transposed conv's input                                           */
   int32_t cout_real;    /* 1..3                                                                     */
   int32_t lr_scale;     /* 2 or 4: output size / lr size                                            */
   int32_t up_mode;      /* TG_UP_*                                                                  */
   int32_t max_ctas;     /* 0 = one persistent CTA per SM                                            */
+  int32_t accumulate;   /* != 0: y already holds upsample_func(lr_curr) (tg_upsample_nchw_f32): out = y + conv +
+                           bias -- one coalesced read per pixel instead of the in-kernel gathers (lr must be NULL) */
   int32_t reserved;     /* must be 0                                                                */
 } tg_tail_desc;
 int tg_convT_convout_tcgen05(const tg_tail_desc* d, void* stream);

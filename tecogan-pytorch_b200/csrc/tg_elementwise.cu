@@ -529,6 +529,11 @@ downsample_bd_kernel(const float* __restrict__ x, const float* __restrict__ k2d,
   y[((size_t)plane * oh + oy) * ow + ox] = acc;
 }
 
+}  // namespace
+cudaError_t tg_warp_w_launch(const float* hr_prev, const float* flow, const float* lr_curr, __half* out, int n, int h,
+                             int w, int h8, int w8, int s, int fm, int cpad, cudaStream_t st);   // tg_warp_w.cu
+namespace {
+
 inline int grid_for(size_t total, int block) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 32;
@@ -565,6 +570,15 @@ static int warp_launch(const float* hr_prev, const float* flow, const float* lr_
   __half* o = (__half*)out;
   TG_REQUIRE(s * h >= 2 && s * w >= 2, TG_E_UNSUPPORTED, "warp_s2d_concat: HR image smaller than 2x2");
   const int fm = !lrflow ? 0 : (up_mode == TG_UP_BICUBIC ? 1 : 2);
+  // default: the warp-autonomous kernel (tg_warp_w.cu); TG_WARP_KERNEL=cta selects the CTA-lock-step one
+  static int use_cta = -1;
+  if (use_cta < 0) { const char* e = getenv("TG_WARP_KERNEL"); use_cta = (e && e[0] == 'c') ? 1 : 0; }
+  if (c == 3 && !use_cta) {
+    cudaError_t le = tg_warp_w_launch(hr_prev, flow, lr_curr, o, n, h, w, h8, w8, s, fm, cpad, st);
+    TG_REQUIRE(le == cudaSuccess, (int)le, "warp_s2d_concat: launch failed: %s", cudaGetErrorString(le));
+    TG_CUDA_LAUNCH_CHECK("warp_s2d_concat");
+    return TG_OK;
+  }
   // Default: all S HR rows of an LR row per pass (12*S gathers in flight per thread, 5 CTAs/SM).
   // TG_WARP_SP=2: two rows per pass at <= 64 registers (8 CTAs/SM) -- measured NOT faster on B200
   // (34.3 vs 32.0 us per 4-frame launch, profiles/bench_r2a*.json): occupancy is not the limiter.

@@ -57,7 +57,8 @@ class TailDesc(ctypes.Structure):
         ('x', c_void_p), ('w_up', c_void_p), ('b_up', c_void_p), ('w_out', c_void_p), ('b_out', c_void_p),
         ('lr', c_void_p), ('y', c_void_p), ('y_u8', c_void_p),
         ('n', c_int32), ('h', c_int32), ('w', c_int32), ('cout_real', c_int32),
-        ('lr_scale', c_int32), ('up_mode', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
+        ('lr_scale', c_int32), ('up_mode', c_int32), ('max_ctas', c_int32), ('accumulate', c_int32),
+        ('reserved', c_int32),
     ]
 
 

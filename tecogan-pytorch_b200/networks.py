@@ -190,14 +190,23 @@ class SRNet(nn.Module):
                 a = body[2 + 2 * i](t, residual=a)
         ups = [c.get(('up', u), self.conv_up[u], L.CONVT_3X3_S2, _RELU) for u in range(0, len(self.conv_up), 2)]
         pc_out = c.get('out', self.conv_out, L.CONV_3X3, L.ACT_NONE, L.EPI_OUT_NCHW_F32)
-        if (ops.tail_enabled() and ops.default_conv_impl() == 'tcgen05' and ups[-1].cin == 64 and ups[-1].cout == 64
+        tail = ops.tail_mode()
+        if (tail and ops.default_conv_impl() == 'tcgen05' and ups[-1].cin == 64 and ups[-1].cout == 64
                 and pc_out.cin == 64 and pc_out.cout_real <= 3):
-            # last transposed conv + ReLU + conv_out + `+= upsample_func(lr_curr)` (+ uint8) in ONE launch: the
-            # 64-channel HR map (88 MB per frame) never reaches HBM
+            # last transposed conv + ReLU + conv_out + residual in ONE launch: the 64-channel HR map (88 MB per
+            # frame) never reaches HBM.  mode 'acc': `out` is first filled with upsample_func(lr_curr) by the
+            # (pure-write) upsample kernel and the tail accumulates onto it -- one coalesced read per pixel;
+            # mode 'fused': the residual (and the uint8 frame) are evaluated inside the tail kernel.
             for up in ups[:-1]:
                 a = up(a)
-            return ops.fused_tail(ups[-1], pc_out, a, lr_curr, self.scale, up_mode_of(self.upsample_func), y=out,
-                                  y_u8=out_u8)
+            mode = up_mode_of(self.upsample_func)
+            if tail == 'acc':
+                out = ops.upsample(lr_curr, self.scale, mode, y=out)
+                out = ops.fused_tail(ups[-1], pc_out, a, None, self.scale, mode, y=out, accumulate=True)
+                if out_u8 is not None:
+                    ops.float_to_uint8_nhwc(out, out_u8)
+                return out
+            return ops.fused_tail(ups[-1], pc_out, a, lr_curr, self.scale, mode, y=out, y_u8=out_u8)
         for up in ups:
             a = up(a)
         # out = conv_out(a) (pure-store epilogue), then out += upsample_func(lr_curr).

@@ -189,7 +189,7 @@ class ConvChain:
         return buffers[self.specs[-1][2]]
 
 
-def fused_tail(up, outc, x, lr_curr, lr_scale, up_mode, y=None, y_u8=None, max_ctas=0):
+def fused_tail(up, outc, x, lr_curr, lr_scale, up_mode, y=None, y_u8=None, max_ctas=0, accumulate=False):
     """SRNet tail in one launch (tg_convT_convout_tcgen05): y = conv_out(relu(convT(x))) + upsample_func(lr_curr)
     [, y_u8 = float32_to_uint8(y) as NHWC].  `up` / `outc` are the PackedConv objects of the last transposed
     conv and of conv_out (their packed weights are used as they are)."""
@@ -218,14 +218,19 @@ def fused_tail(up, outc, x, lr_curr, lr_scale, up_mode, y=None, y_u8=None, max_c
             raise L.TecoganB200Error(f'fused tail: uint8 output shape {tuple(y_u8.shape)}')
         d.y_u8 = y_u8.data_ptr()
     d.n, d.h, d.w, d.cout_real, d.lr_scale, d.up_mode, d.max_ctas, d.reserved = n, h, w, co, lr_scale, up_mode, max_ctas, 0
+    d.accumulate = 1 if accumulate else 0
     L.check(L.load().tg_convT_convout_tcgen05(ctypes.byref(d), _stream()), 'tg_convT_convout_tcgen05')
     return y
 
 
-def tail_enabled():
-    """TECOGAN_B200_TAIL=0 runs the last transposed conv, conv_out, the residual upsample and the uint8
-    conversion as four launches instead of tg_convT_convout_tcgen05 (A/B measurements)."""
-    return os.environ.get('TECOGAN_B200_TAIL', '0') != '0'      # TODO(flip to '1' once validated on a B200)
+def tail_mode():
+    """TECOGAN_B200_TAIL: '0' = last transposed conv, conv_out, residual upsample and uint8 as four launches;
+    'acc' = tg_convT_convout_tcgen05 accumulating onto a pre-written residual; 'fused' = residual and uint8
+    evaluated inside the tail kernel.  Default 'acc': measured 0.786 ms per step against 0.849 ('0') and 0.897
+    ('fused': the in-kernel gathers and 2-byte uint8 stores sit on the epilogue's critical path) --
+    profiles/bench_r2f_tail_*.json."""
+    v = os.environ.get('TECOGAN_B200_TAIL', 'acc')
+    return {'0': None, '': None, '1': 'fused', 'fused': 'fused', '2': 'acc', 'acc': 'acc'}[v]
 
 
 def chain_enabled():

@@ -1122,7 +1122,7 @@ def check_st_discriminator_input():
     return out
 
 
-def check_fused_tail(scale=4, n=2, h=20, w=26, with_lr=True, seed=400):
+def check_fused_tail(scale=4, n=2, h=20, w=26, with_lr=True, seed=400, accumulate=False):
     """tg_convT_convout_tcgen05 (last transposed conv + ReLU + conv_out + upsample_func(lr) + uint8 in one
     launch) against the same four stages run as separate kernels, and against torch CPU fp32."""
     mid_h, mid_w = h, w                               # input of the last transposed conv
@@ -1146,7 +1146,12 @@ def check_fused_tail(scale=4, n=2, h=20, w=26, with_lr=True, seed=400):
     # fused (output buffers poisoned first: every pixel must be written exactly once)
     got = torch.full((n, 3, 2 * mid_h, 2 * mid_w), float('nan'), device=DEV)
     got_u8 = torch.full((n, 2 * mid_h, 2 * mid_w, 3), 77, dtype=torch.uint8, device=DEV)
-    ops.fused_tail(up, oc, xg, lr.to(DEV) if with_lr else None, lr_scale, mode, y=got, y_u8=got_u8)
+    if accumulate:       # y pre-filled with the residual, the kernel adds conv + bias onto it (no uint8 inside)
+        ops.upsample(lr.to(DEV), lr_scale, mode, y=got)
+        ops.fused_tail(up, oc, xg, None, lr_scale, mode, y=got, accumulate=True)
+        ops.float_to_uint8_nhwc(got, got_u8)
+    else:
+        ops.fused_tail(up, oc, xg, lr.to(DEV) if with_lr else None, lr_scale, mode, y=got, y_u8=got_u8)
     torch.cuda.synchronize()
     assert not torch.isnan(got).any(), 'fused tail left output pixels unwritten'
     out = {'vs_separate_max_abs': float((got - ref).abs().max()), 'vs_separate_rel_l2': rell2(got.cpu().numpy(), ref.cpu().numpy())}
@@ -1221,6 +1226,8 @@ CHECKS = {
     'fused_tail_bd4_ragged_1img': lambda: check_fused_tail(4, n=1, h=30, w=14, seed=410),
     'fused_tail_bd4_big': lambda: check_fused_tail(4, n=2, h=64, w=46, seed=420),
     'fused_tail_bi2': lambda: check_fused_tail(2, n=3, h=21, w=33, seed=430),
+    'fused_tail_accumulate_bd4': lambda: check_fused_tail(4, n=2, h=34, w=22, seed=450, accumulate=True),
+    'fused_tail_accumulate_bi2': lambda: check_fused_tail(2, n=1, h=17, w=31, seed=460, accumulate=True),
     'fused_tail_no_residual': lambda: check_fused_tail(4, with_lr=False, h=18, w=8, seed=440),
     'autograd_guards': check_autograd_guards,
     'dgrad_simt_conv': lambda: check_conv_dgrad('simt'),

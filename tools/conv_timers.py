@@ -127,7 +127,7 @@ TAIL_NAMES = ['mma_wait_full', 'mma_wait_tempty', 'mma_wait_hrfull', 'mma_wait_d
               'kernel', 'tiles']
 
 
-def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True):
+def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True, accumulate=False):
     """per-role cycles of tail_tcgen05_kernel (fused ConvT + conv_out + residual + uint8), per tile"""
     dev = 'cuda:0'
     os.environ['TG_TAIL_FLAGS'] = flags
@@ -138,25 +138,26 @@ def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True):
     lr = torch.rand(n, 3, h // 2, w // 2, device=dev) if with_lr else None
     y = torch.zeros(n, 3, 2 * h, 2 * w, device=dev)
     u8 = torch.zeros(n, 2 * h, 2 * w, 3, dtype=torch.uint8, device=dev) if with_u8 else None
+    call = lambda: ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8, accumulate=accumulate)
     for _ in range(3):
-        ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+        call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+    call()
     e1.record()
     torch.cuda.synchronize()
     us_plain = e0.elapsed_time(e1) * 1e3
     buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     lib = L.load()
     lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
-    ops.fused_tail(up, oc, x, lr, 4, L.UP_BICUBIC, y=y, y_u8=u8)
+    call()
     torch.cuda.synchronize()
     lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
     t = buf.view(148, 16).cpu().double()
     t = t[t[:, 13] > 0]
     tiles = t[:, 14].mean().item()
-    out = {'flags': flags, 'lr': with_lr, 'u8': with_u8, 'us': round(us_plain, 1), 'tiles_per_cta': tiles,
+    out = {'flags': flags, 'lr': with_lr, 'u8': with_u8, 'accumulate': accumulate, 'us': round(us_plain, 1), 'tiles_per_cta': tiles,
            'per_tile': {nm: round(t[:, i].mean().item() / max(tiles, 1)) for i, nm in enumerate(TAIL_NAMES[:14])}}
     print(json.dumps(out), flush=True)
     return out
@@ -164,11 +165,10 @@ def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True):
 
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'tail':
-        run_tail('0')
-        run_tail('1')            # no residual
-        run_tail('3')            # no residual, no uint8
-        run_tail('7')            # + no exchange (wrong results: timing only)
-        run_tail('0', with_lr=False, with_u8=False)
+        run_tail('0')                                            # residual + uint8 inside the kernel
+        run_tail('0', with_u8=False)                             # residual inside
+        run_tail('0', with_lr=False, with_u8=False)              # conv only
+        run_tail('0', with_lr=False, with_u8=False, accumulate=True)   # accumulate onto a pre-written residual
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'chain':
         run_chain()

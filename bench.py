@@ -355,6 +355,43 @@ def _generator_only_ms(generator, device, batch, reps=3):
     return statistics.median(out)
 
 
+def time_train_kernels(dev, pk, batch):
+    """Live CUDA-event timing of the two tensor-core kernels of the backward on the training shapes: the weight
+    gradient of a 64->64 residual conv over all T*n images of a step (one launch per layer and step) and its data
+    gradient on one frame's batch.  FLOPs by the reference counter's convention (2*9*Cin*Cout per pixel)."""
+    import torch
+    ops = sys.modules['tecogan-pytorch_b200.ops']
+    L = sys.modules['tecogan-pytorch_b200.lib']
+    c, h, w = TRAIN['lr']
+    T_ = 2 * TRAIN['t'] - 1
+    wt = torch.randn(64, 64, 3, 3, device=dev) * 0.04
+    pc = ops.PackedConv(wt, torch.zeros(64, device=dev), L.CONV_3X3, L.ACT_RELU)
+    dgr = ops.PackedDgrad(pc, wt)
+    out = {}
+    n_img = T_ * batch
+    xs = [torch.randn(n_img, h, w, 64, device=dev).half() for _ in range(2)]         # 2 x 319 MB > L2
+    dzs = [torch.randn(n_img, h, w, 64, device=dev).half() for _ in range(2)]
+    dw = torch.zeros(64, 64, 3, 3, device=dev)
+    t = _time_graph(lambda i: ops.wgrad(pc, xs[i], dzs[i], dw), 2, 6, torch)
+    fl = RES_CONV_FLOP_PER_PX * n_img * h * w
+    out['roofline_wgrad'] = {'kernel': f'wgrad_tcgen05_kernel<conv3x3> (64->64, {n_img} images {h}x{w} = one layer of one step)',
+                             'bound': 'tensor', 'achieved': fl / t / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
+                             'frac': fl / t / 1e12 / pk['tflops_burst'], 'us_per_launch': t * 1e6, 'flop_per_launch': fl,
+                             'traffic': ncu_traffic('wgrad_train')[0], 'traffic_src': ncu_traffic('wgrad_train')[1],
+                             'how': '6 launches in one CUDA graph over 2 rotating operand sets (1.3 GB > L2), CUDA events'}
+    nb = 8
+    xd = [torch.randn(batch, h, w, 64, device=dev).half() for _ in range(nb)]
+    yd = [torch.empty_like(v) for v in xd]
+    md = [torch.randn(batch, h, w, 64, device=dev).half() for _ in range(nb)]
+    t = _time_graph(lambda i: dgr(xd[i], y=yd[i], mask=md[i], mask_act=L.ACT_RELU), nb, 40, torch)
+    fl = RES_CONV_FLOP_PER_PX * batch * h * w
+    out['roofline_dgrad'] = {'kernel': f'conv_tcgen05_kernel<conv3x3, halo, BWD> (dgrad 64->64 * ReLU\'(mask), {batch} images {h}x{w})',
+                             'bound': 'tensor', 'achieved': fl / t / 1e12, 'peak': pk['tflops_burst'], 'unit': 'TFLOP/s',
+                             'frac': fl / t / 1e12 / pk['tflops_burst'], 'us_per_launch': t * 1e6, 'flop_per_launch': fl,
+                             'traffic': None, 'how': f'40 launches in one CUDA graph over {nb} rotating buffer sets, CUDA events'}
+    return out
+
+
 def run_train(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -446,6 +483,8 @@ def run_train(args, rank, world, local_rank):
             line['impl'] = 'eager-gpu'
     del m
     torch.cuda.empty_cache()
+    if rank == 0 and impl == 'ours':
+        line.update(time_train_kernels(dev, peaks(), batch))
     if rank == 0 and world == 1 and impl == 'ours' and not args.no_eager:
         gb = min(batch, 8)
         ours_ms = _generator_only_ms('ours', dev, gb)

@@ -45,29 +45,83 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
   __syncwarp();
 
   const long long wstride = (long long)gridDim.x * kWarpsPerCta;
-  for (long long u = (long long)blockIdx.x * kWarpsPerCta + warp; u < units; u += wstride) {
+  // Software pipeline over units: the (small) flow and lr_curr reads of unit u+1 are issued while unit u gathers,
+  // so a unit costs ONE dependent DRAM round trip (the gathers) instead of two.
+  constexpr int NF = LRFLOW ? (2 * FH * FW + 31) / 32 : 2 * S;     // prefetched flow values per lane
+  constexpr int NL = (LRW * 3 + 31) / 32;                         // prefetched lr_curr values per lane
+  float pf[NF], pl[NL];
+  auto prefetch = [&](long long u) {
+    const int xb = (int)(u % xblocks);
+    const int y = (int)((u / xblocks) % h);
+    const int nn = (int)(u / ((long long)xblocks * h));
+    const int x0 = xb * LRW;
+    if (LRFLOW) {
+      // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int i = lane + 32 * j;
+        float v = 0.f;
+        if (i < 2 * FH * FW) {
+          const int col = i % FW, row = (i / FW) % FH, comp = i / (FH * FW);
+          const int yy = tg_reflect_hi(tg_clampi(y - 1 + row, 0, h - 1), h8);
+          const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), w8);
+          v = __ldg(flow + (((size_t)nn * 2 + comp) * h8 + yy) * w8 + xx);
+        }
+        pf[j] = v;
+      }
+    } else {
+      const int X = x0 * S + lane;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) pf[j] = 0.f;
+      if (X < W) {
+        const float* f0 = flow + (((size_t)nn * 2 + 0) * H + (size_t)y * S) * W + X;
+        const float* f1 = flow + (((size_t)nn * 2 + 1) * H + (size_t)y * S) * W + X;
+#pragma unroll
+        for (int sy = 0; sy < S; ++sy) {
+          pf[sy] = __ldg(f0 + (size_t)sy * W);
+          pf[S + sy] = __ldg(f1 + (size_t)sy * W);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = lane + 32 * j;
+      float v = 0.f;
+      if (i < LRW * 3) {
+        const int k = i / LRW, p = i - k * LRW;
+        if (x0 + p < w) v = __ldg(lr_curr + (((size_t)nn * 3 + k) * h + y) * w + x0 + p);
+      }
+      pl[j] = v;
+    }
+  };
+  const long long u_first = (long long)blockIdx.x * kWarpsPerCta + warp;
+  if (u_first < units) prefetch(u_first);
+  for (long long u = u_first; u < units; u += wstride) {
     const int xb = (int)(u % xblocks);
     const int y = (int)((u / xblocks) % h);
     const int nn = (int)(u / ((long long)xblocks * h));
     const int x0 = xb * LRW;
     const int X = x0 * S + lane;
     float uu[S], vv[S];
+    // hand the prefetched values over (shared memory for the LR flow neighbourhood and the lr channels) ...
     if (LRFLOW) {
-      // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
-      for (int i = lane; i < 2 * FH * FW; i += 32) {
-        const int col = i % FW, row = (i / FW) % FH, comp = i / (FH * FW);
-        const int yy = tg_reflect_hi(tg_clampi(y - 1 + row, 0, h - 1), h8);
-        const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), w8);
-        fsrc[i] = __ldg(flow + (((size_t)nn * 2 + comp) * h8 + yy) * w8 + xx);
+#pragma unroll
+      for (int j = 0; j < NF; ++j)
+        if (lane + 32 * j < 2 * FH * FW) fsrc[lane + 32 * j] = pf[j];
+    } else {
+#pragma unroll
+      for (int sy = 0; sy < S; ++sy) { uu[sy] = pf[sy]; vv[sy] = pf[S + sy]; }
+    }
+#pragma unroll
+    for (int j = 0; j < NL; ++j) {
+      const int i = lane + 32 * j;
+      if (i < LRW * 3) {
+        const int k = i / LRW, p = i - k * LRW;
+        tile[p * tstride + k] = __float2half(pl[j]);
       }
     }
-    // lr_curr channels of the unit's pixels
-    for (int i = lane; i < LRW * 3; i += 32) {
-      const int k = i / LRW, p = i - k * LRW;
-      float v = 0.f;
-      if (x0 + p < w) v = __ldg(lr_curr + (((size_t)nn * 3 + k) * h + y) * w + x0 + p);
-      tile[p * tstride + k] = __float2half(v);
-    }
+    // ... and start the next unit's reads before this unit's gathers
+    if (u + wstride < units) prefetch(u + wstride);
     if (LRFLOW) {
       __syncwarp();
       float kx[4], hx[2][FH];
@@ -85,14 +139,6 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
         tg_up_taps(up_mode, sy, S, ky);
         uu[sy] = (float)S * (ky[0] * hx[0][0] + ky[1] * hx[0][1] + ky[2] * hx[0][2] + ky[3] * hx[0][3]);
         vv[sy] = (float)S * (ky[0] * hx[1][0] + ky[1] * hx[1][1] + ky[2] * hx[1][2] + ky[3] * hx[1][3]);
-      }
-    } else if (X < W) {
-      const float* f0 = flow + (((size_t)nn * 2 + 0) * H + (size_t)y * S) * W + X;
-      const float* f1 = flow + (((size_t)nn * 2 + 1) * H + (size_t)y * S) * W + X;
-#pragma unroll
-      for (int sy = 0; sy < S; ++sy) {
-        uu[sy] = __ldg(f0 + (size_t)sy * W);
-        vv[sy] = __ldg(f1 + (size_t)sy * W);
       }
     }
     if (X < W) {

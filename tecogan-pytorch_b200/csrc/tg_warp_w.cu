@@ -7,7 +7,11 @@
 // warps in lock step (two __syncthreads per LR row), so while one phase waits on DRAM nothing else of that
 // CTA is in flight: ncu showed it latency-bound at 14 % DRAM throughput, and doubling the occupancy by
 // halving the loads per thread did not help (profiles/bench_r2a*.json).  Here warps drift apart and the
-// gathers of one overlap the stores / flow staging of the others; units are handed out grid-stride.
+// gathers of one overlap the stores / flow staging of the others; units are handed out grid-stride, and the
+// small flow / lr reads of the next unit are prefetched into registers so a unit costs one dependent DRAM
+// round trip: 27.8 us per 4-frame launch against 31.9 (profiles/bench_r2j_*.json).  A third variant that
+// issued the corner gathers of the next unit as 4-byte cp.async into a double-buffered shared-memory
+// array (no registers held) was measured at 46.5 us -- twice the LSU work per gather -- and removed.
 #include "tg_common.cuh"
 
 #include <cstdlib>
@@ -187,6 +191,7 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
     __syncwarp();        // the tile and fsrc are rewritten by the next unit
   }
 }
+
 
 }  // namespace
 

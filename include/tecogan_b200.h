@@ -57,7 +57,10 @@ enum { TG_UP_BICUBIC = 0, TG_UP_BILINEAR = 1 };
 enum {
   TG_EPI_NHWC_F16 = 0,      /* y = act(conv + bias) [+ residual]  -> NHWC fp16        */
   TG_EPI_FLOW_NCHW_F32 = 1, /* y = 24*tanh(conv + bias)           -> NCHW fp32 [N,2,H,W] */
-  TG_EPI_OUT_NCHW_F32 = 2   /* y = conv + bias                    -> NCHW fp32 [N,C,H,W] */
+  TG_EPI_OUT_NCHW_F32 = 2,  /* y = conv + bias                    -> NCHW fp32 [N,C,H,W] */
+  TG_EPI_NHWC_F16_POOL2 = 3 /* y = maxpool2x2(act(conv + bias))   -> NHWC fp16 [n,h/2,w/2,cout]: nn.MaxPool2d(2,2)
+                               (tecogan_nets.py:28,35,42) folded into the producing conv's epilogue (tcgen05 kernel,
+                               conv3x3 only, no residual); the full-resolution map is never written */
 };
 enum { TG_AMODE_AUTO = 0, TG_AMODE_HALO = 1, TG_AMODE_TAP = 2 };
 

@@ -181,6 +181,7 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who);
 int tg_conv_simt(const tg_conv_desc* d, void* stream) {
   int rc = tg_conv_validate(d, "conv_simt");
   if (rc != TG_OK) return rc;
+  TG_REQUIRE(d->epilogue != TG_EPI_NHWC_F16_POOL2, TG_E_UNSUPPORTED, "conv_simt: pooled epilogue is tcgen05-only");
   const int n_acc = d->kind == TG_CONVT_3X3_S2 ? 4 : 1;
   const size_t total = (size_t)d->n * d->h * d->w * n_acc *
                        (d->epilogue != TG_EPI_NHWC_F16 ? 1 : d->cout / 8);

@@ -98,7 +98,9 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
 // BWD = data-gradient instantiation: epilogue y = (acc + bias [+ residual]) * act'(mask)  (TG_ACT_DRELU /
 // TG_ACT_DLRELU02; TG_ACT_NONE = no derivative).  Kept out of the forward instantiations so their
 // register allocation and code are untouched.
-template <int KIND, int MODE, bool TIMING, bool BWD = false>
+// POOL = TG_EPI_NHWC_F16_POOL2 instantiation: 2x2 max over the tile's pixels by warp shuffles (lane ^ 1 = x
+// neighbour, lane ^ 8 = y neighbour: a warp holds four 8-pixel rows of the 16x8 tile), one store per 2x2 block.
+template <int KIND, int MODE, bool TIMING, bool BWD = false, bool POOL = false>
 __global__ void __launch_bounds__(conv_threads(KIND, MODE), 1)
 conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -501,13 +503,14 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
       TG_ACC(te_tfull, t_s);
       t_s = TG_T0();
       tc_fence_after();
-      if (d.epilogue == TG_EPI_NHWC_F16) {
+      if (d.epilogue == TG_EPI_NHWC_F16 || POOL) {
         // Each thread owns one output pixel = 64 channels = one contiguous 128-byte NHWC row: it
         // goes straight from registers to global memory (8 x 16-byte stores complete the line),
         // so the epilogue costs no shared-memory bandwidth -- the MMA operand reads need all of it.
         for (int acc = acc_lo; acc < acc_hi; ++acc) {
           int oy = py, ox = px, OW = d.w, OH = d.h;
           if (KIND == TG_CONVT_3X3_S2) { oy = 2 * py + (acc >> 1); ox = 2 * px + (acc & 1); OW = 2 * d.w; OH = 2 * d.h; }
+          if (POOL) { OH = d.h >> 1; OW = d.w >> 1; oy = py >> 1; ox = px >> 1; }
           uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(d.y) +
                                                  (((size_t)tc.n * OH + oy) * OW + ox) * d.cout + tc.nb * p.bn);
 #pragma unroll
@@ -555,7 +558,27 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
                 o[j] = __floats2half2_rn(a0, a1);
               }
             }
-            if (inb) {
+            if (POOL) {
+              // max over the 2x2 block (all 32 lanes take part; floor pooling: blocks that reach outside the
+              // image are not stored, so out-of-range pixels never contribute to a stored value)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint32_t* wv = reinterpret_cast<uint32_t*>(&ov[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint32_t o1 = __shfl_xor_sync(0xFFFFFFFFu, wv[j], 1);
+                  __half2 mx = __hmax2(*reinterpret_cast<__half2*>(&wv[j]), *reinterpret_cast<__half2*>(&o1));
+                  uint32_t m32 = *reinterpret_cast<uint32_t*>(&mx);
+                  uint32_t o8 = __shfl_xor_sync(0xFFFFFFFFu, m32, 8);
+                  mx = __hmax2(mx, *reinterpret_cast<__half2*>(&o8));
+                  wv[j] = *reinterpret_cast<uint32_t*>(&mx);
+                }
+              }
+              if (((tx | ty) & 1) == 0 && py + 1 < d.h && px + 1 < d.w) {
+                st_global_256(orow + pc * 4, ov[0], ov[1]);
+                st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
+              }
+            } else if (inb) {
               st_global_256(orow + pc * 4, ov[0], ov[1]);
               st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
             }
@@ -680,7 +703,10 @@ int tg_conv_validate(const tg_conv_desc* d, const char* who) {
              "%s: conv3x3s2 needs the NHWC epilogue", who);
   TG_REQUIRE(d->cin == 64 || d->cin == 128 || d->cin == 256, TG_E_UNSUPPORTED,
              "%s: cin=%d (stored channels must be 64, 128 or 256)", who, d->cin);
-  if (d->epilogue == TG_EPI_NHWC_F16) {
+  if (d->epilogue == TG_EPI_NHWC_F16_POOL2)
+    TG_REQUIRE(d->kind == TG_CONV_3X3 && d->residual == nullptr && d->act <= TG_ACT_LRELU02 && d->h >= 2 && d->w >= 2,
+               TG_E_UNSUPPORTED, "%s: the pooled epilogue needs a conv3x3 without residual / derivative epilogue", who);
+  if (d->epilogue == TG_EPI_NHWC_F16 || d->epilogue == TG_EPI_NHWC_F16_POOL2) {
     TG_REQUIRE(d->cout == 64 || d->cout == 128 || d->cout == 256, TG_E_UNSUPPORTED,
                "%s: cout=%d (64, 128 or 256 for the NHWC epilogue)", who, d->cout);
     TG_REQUIRE(!(d->residual && d->kind == TG_CONVT_3X3_S2), TG_E_UNSUPPORTED, "%s: residual with convT", who);
@@ -706,7 +732,8 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   KParams p;
   p.d = *d;
   p.dbg = g_conv_timers;
-  const bool tapn = d->epilogue != TG_EPI_NHWC_F16;
+  const bool tapn = d->epilogue == TG_EPI_FLOW_NCHW_F32 || d->epilogue == TG_EPI_OUT_NCHW_F32;
+  const bool pool = d->epilogue == TG_EPI_NHWC_F16_POOL2;
   p.step_y = tapn ? kTapnStepY : TH;
   p.step_x = tapn ? kTapnStepX : TW;
   p.tiles_x = tg_ceil_div(d->w, p.step_x);
@@ -816,6 +843,12 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
     TG_SET_ATTR(TG_CONV_3X3, MODE_HALO) TG_SET_ATTR(TG_CONV_3X3, MODE_TAP) TG_SET_ATTR(TG_CONV_3X3, MODE_TAPN)
     TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_HALO) TG_SET_ATTR(TG_CONVT_3X3_S2, MODE_TAP)
 #undef TG_SET_ATTR
+#define TG_SET_ATTR_POOL(H)                                                                                                  \
+    e = cudaFuncSetAttribute(conv_tcgen05_kernel<TG_CONV_3X3, H, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)kSmemLimit);                                                                               \
+    if (e != cudaSuccess) err = e;
+    TG_SET_ATTR_POOL(MODE_HALO) TG_SET_ATTR_POOL(MODE_TAP)
+#undef TG_SET_ATTR_POOL
 #define TG_SET_ATTR_BWD(K, H)                                                                                  \
     e = cudaFuncSetAttribute(conv_tcgen05_kernel<K, H, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              (int)kSmemLimit);                                                                 \
@@ -839,7 +872,12 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t lerr = cudaSuccess;
   const bool bwd = d->act >= TG_ACT_DRELU || d->kind == TG_CONV_3X3_S2;
-  if (bwd) {
+  if (pool) {
+    if (p.halo)
+      lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_HALO, false, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_HALO)), kSmemLimit, st, map_a, p);
+    else
+      lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3, MODE_TAP, false, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3, MODE_TAP)), kSmemLimit, st, map_a, p);
+  } else if (bwd) {
     if (d->kind == TG_CONV_3X3_S2)
       lerr = tg_launch(conv_tcgen05_kernel<TG_CONV_3X3_S2, MODE_TAP, false, true>, dim3(grid), dim3(conv_threads(TG_CONV_3X3_S2, MODE_TAP)), kSmemLimit, st, map_a, p);
     else if (p.halo)

@@ -16,7 +16,7 @@ TG_OK = 0
 ACT_NONE, ACT_RELU, ACT_LRELU02, ACT_DRELU, ACT_DLRELU02 = 0, 1, 2, 3, 4
 CONV_3X3, CONVT_3X3_S2, CONV_3X3_S2 = 0, 1, 2
 UP_BICUBIC, UP_BILINEAR = 0, 1
-EPI_NHWC_F16, EPI_FLOW_NCHW_F32, EPI_OUT_NCHW_F32 = 0, 1, 2
+EPI_NHWC_F16, EPI_FLOW_NCHW_F32, EPI_OUT_NCHW_F32, EPI_NHWC_F16_POOL2 = 0, 1, 2, 3
 AMODE_AUTO, AMODE_HALO, AMODE_TAP = 0, 1, 2
 
 

@@ -107,10 +107,14 @@ class FNet(nn.Module):
             from .autograd import FNetFunction
             return FNetFunction.apply(self, x1, x2, *self.parameters())
         a = ops.pack_pair(x1, x2)                       # cat + NHWC fp16 (c64)
+        fuse_pool = ops.default_conv_impl() == 'tcgen05' and ops.pool_fused()
         for name, _, _ in self.ENC:
             a = self._conv(name, 0, _LRELU)(a)
-            a = self._conv(name, 2, _LRELU)(a)
-            a = ops.maxpool2x2(a)
+            if fuse_pool:                               # MaxPool2d(2,2) in the conv's epilogue (inference only:
+                a = self._conv(name, 2, _LRELU)(a, pool=True)   # training keeps the full-resolution map)
+            else:
+                a = self._conv(name, 2, _LRELU)(a)
+                a = ops.maxpool2x2(a)
         for name, _, _ in self.DEC:
             a = self._conv(name, 0, _LRELU)(a)
             a = self._conv(name, 2, _LRELU)(a)

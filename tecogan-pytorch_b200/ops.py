@@ -104,13 +104,18 @@ class PackedConv:
             return (n, h, w, self.cout), torch.float16
         return (n, self.cout_real, h, w), torch.float32
 
-    def __call__(self, x, y=None, residual=None, impl=None, a_mode=None, max_ctas=0):
-        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None)."""
+    def __call__(self, x, y=None, residual=None, impl=None, a_mode=None, max_ctas=0, pool=False):
+        """x NHWC fp16 [n,h,w,cin] -> y (allocated when None).  pool=True: nn.MaxPool2d(2,2) folded into the
+        epilogue, y = [n,h//2,w//2,cout] (conv3x3 layers with the NHWC epilogue, tcgen05 only)."""
         _req(x, torch.float16, 'conv input', 4)
         n, h, w, cin = x.shape
         if cin != self.cin:
             raise L.TecoganB200Error(f'conv input has {cin} channels, layer expects {self.cin}')
         shape, dtype = self.out_shape(n, h, w)
+        if pool:
+            if self.epilogue != L.EPI_NHWC_F16 or self.kind != L.CONV_3X3 or residual is not None:
+                raise L.TecoganB200Error('pooled epilogue: conv3x3 with the NHWC epilogue and no residual only')
+            shape = (n, h // 2, w // 2, self.cout)
         if y is None:
             y = torch.empty(shape, dtype=dtype, device=x.device)
         else:
@@ -126,7 +131,7 @@ class PackedConv:
         d.residual = residual.data_ptr() if residual is not None else None
         d.y = y.data_ptr()
         d.n, d.h, d.w, d.cin, d.cout, d.cout_real = n, h, w, self.cin, self.cout, self.cout_real
-        d.kind, d.act, d.epilogue = self.kind, self.act, self.epilogue
+        d.kind, d.act, d.epilogue = self.kind, self.act, (L.EPI_NHWC_F16_POOL2 if pool else self.epilogue)
         d.a_mode = default_a_mode() if a_mode is None else a_mode
         d.max_ctas = max_ctas
         impl = impl or default_conv_impl()
@@ -231,6 +236,12 @@ def tail_mode():
     profiles/bench_r2f_tail_*.json."""
     v = os.environ.get('TECOGAN_B200_TAIL', 'acc')
     return {'0': None, '': None, '1': 'fused', 'fused': 'fused', '2': 'acc', 'acc': 'acc'}[v]
+
+
+def pool_fused():
+    """TECOGAN_B200_POOL=0 runs FNet's three max-pools as their own kernels instead of in the epilogue of the
+    conv that feeds them (A/B measurements; bit-identical output)."""
+    return os.environ.get('TECOGAN_B200_POOL', '1') != '0'
 
 
 def chain_enabled():

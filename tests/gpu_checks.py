@@ -1122,6 +1122,23 @@ def check_st_discriminator_input():
     return out
 
 
+def check_conv_pool_epilogue(cin=64, cout=64, h=37, w=45, n=2, a_mode=None, seed=500):
+    """TG_EPI_NHWC_F16_POOL2 (MaxPool2d(2,2) folded into the conv epilogue by warp shuffles) must equal the
+    separate maxpool kernel applied to the plain conv output bit for bit (odd sizes: floor pooling)."""
+    x = rand(seed, n, cin, h, w, lo=-1, hi=1)
+    wt = rand(seed + 1, cout, cin, 3, 3, lo=-0.1, hi=0.1)
+    b = rand(seed + 2, cout, lo=-0.2, hi=0.2)
+    pc = ops.PackedConv(wt.to(DEV), b.to(DEV), L.CONV_3X3, L.ACT_LRELU02)
+    xg = nhwc(x, ops.pad64(cin))
+    ref = ops.maxpool2x2(pc(xg, a_mode=a_mode))
+    got = torch.full((n, h // 2, w // 2, pc.cout), float('nan'), dtype=torch.float16, device=DEV)
+    pc(xg, y=got, a_mode=a_mode, pool=True)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got).any(), 'pooled epilogue left pixels unwritten'
+    assert torch.equal(got, ref), float((got.float() - ref.float()).abs().max())
+    return {'bit_exact': True, 'shape': list(got.shape)}
+
+
 def check_fused_tail(scale=4, n=2, h=20, w=26, with_lr=True, seed=400, accumulate=False):
     """tg_convT_convout_tcgen05 (last transposed conv + ReLU + conv_out + upsample_func(lr) + uint8 in one
     launch) against the same four stages run as separate kernels, and against torch CPU fp32."""
@@ -1222,6 +1239,9 @@ CHECKS = {
     'bench_workload_parity': check_bench_workload_parity,
     'bi2_workload_parity': check_bi2_workload_parity,
     'reference_callers_integration': check_reference_callers_integration,
+    'conv_pool_epilogue_halo': check_conv_pool_epilogue,
+    'conv_pool_epilogue_128_tap': lambda: check_conv_pool_epilogue(cin=128, cout=128, h=33, w=80, n=1, seed=510),
+    'conv_pool_epilogue_fullres': lambda: check_conv_pool_epilogue(h=134, w=320, n=2, seed=520),
     'fused_tail_bd4': lambda: check_fused_tail(4),
     'fused_tail_bd4_ragged_1img': lambda: check_fused_tail(4, n=1, h=30, w=14, seed=410),
     'fused_tail_bd4_big': lambda: check_fused_tail(4, n=2, h=64, w=46, seed=420),

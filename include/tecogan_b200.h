@@ -285,6 +285,8 @@ typedef struct tg_wgrad_desc {
                            (convT: [n,2h,2w,cout]), loss-scaled                           */
   float* dw;            /* fp32 gradient, parameter layout                                  */
   const float* scale;   /* {scale, 1/scale} or NULL                                         */
+  float* db;            /* conv3x3 only, may be NULL: bias gradient db[co] += 1/scale * sum_p dz[p][co], computed by
+                           the same MMAs (the unused half of the last tap pair reads a block of ones) */
   int32_t n, h, w;      /* of the layer INPUT                                               */
   int32_t cin, cout;    /* stored channel counts (64/128/256)                               */
   int32_t cin_real, cout_real;

@@ -55,8 +55,8 @@ def _param_grads(pc, module, x, dz, scale, grads):
     if n is not None:                      # [T,n,h,w,c] buffers: one launch over all T*n images
         x = x.view(-1, *x.shape[2:])
         dz = dz.view(-1, *dz.shape[2:])
-    ops.wgrad(pc, x, dz, grads.of(module.weight), scale)
-    ops.bias_grad(dz, grads.of(module.bias), scale)
+    # the bias gradient comes out of the same tcgen05 launch (conv layers) or a separate reduction (transposed convs)
+    ops.wgrad(pc, x, dz, grads.of(module.weight), scale, db=grads.of(module.bias))
 
 
 # ================================================================================ FNet

@@ -51,7 +51,9 @@ struct WParams {
   uint32_t idesc;
   int flags;                 // diagnostics: 1 = swap LBO/SBO fields, 2 = one tap per MMA (two passes)
   float* dw;
+  float* db;                 // bias gradient (conv kind only) or null
   const float* scale;        // device [scale, 1/scale] or null
+  uint32_t off_ones;         // all-ones fp16 region behind the stages (conv kind + db)
 };
 
 // MN-major UMMA shared-memory descriptor, 128B swizzle (cute::UMMA canonical layout
@@ -115,6 +117,15 @@ wgrad_tcgen05_kernel(const __grid_constant__ WParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
+  // Bias gradient for free (conv kind): the unused upper half of the last tap pair (tap 8 + nothing) points its
+  // 64 "input channels" at a region of fp16 ones, so rows 64..127 of that accumulator become sum_p dz[p][co].
+  const bool with_db = KIND == TG_CONV_3X3 && p.db != nullptr;
+  if (with_db) {
+    uint32_t* ones = reinterpret_cast<uint32_t*>(sm + p.off_ones);
+    for (int i = threadIdx.x; i < 2560 / 4; i += kThreads) ones[i] = 0x3C003C00u;   // two K groups, box_row apart
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
   tg_pdl_wait();
   tg_pdl_trigger();
 
@@ -173,7 +184,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ WParams p) {
                 const int o1 = jb.g1 >= 0 ? tap_off<KIND>(jb.g1, 0) : o0 + 1;
                 const int o1w = jb.g1 >= 0 ? tap_off<KIND>(jb.g1, 1) - tap_off<KIND>(jb.g1, 0) : o0w;
                 const uint32_t off0 = (uint32_t)(o0 + o0w * p.box_w) * 128u;
-                const uint32_t lbo = (uint32_t)((o1 + o1w * p.box_w) - (o0 + o0w * p.box_w)) * 128u;
+                uint32_t lbo = (uint32_t)((o1 + o1w * p.box_w) - (o0 + o0w * p.box_w)) * 128u;
+                if (jb.g1 < 0 && with_db) lbo = (base + p.off_ones) - (xrow + off0);    // second chunk = the ones region
                 const int plane = KIND == TG_CONV_3X3 ? 0 : tg_group(KIND, jb.g0).acc;
                 const uint64_t da = swap ? make_sdesc_mn(xrow + off0, box_row, lbo) : make_sdesc_mn(xrow + off0, lbo, box_row);
                 const uint64_t db = swap ? make_sdesc_mn(sdz + plane * kDzTileBytes + ks * 2048u, 1024u, 1024u)
@@ -225,12 +237,20 @@ wgrad_tcgen05_kernel(const __grid_constant__ WParams p) {
             g = (r >> 6) == 0 ? pass * 5 + j : -1;
             if (g >= 9) g = -1;
           }
+          const bool db_rows = with_db && !single && j == 4 && r == 64 && cic == 0;   // one thread per CTA column set
           const TgGroup gr = tg_group(KIND, g < 0 ? 0 : g);
 #pragma unroll
           for (int pc = 0; pc < 2; ++pc) {
             uint32_t v[32];
             tmem_ld32(tmem_base + (uint32_t)j * 64u + pc * 32 + ((uint32_t)(q * 32) << 16), v);
             tmem_ld_wait();
+            if (db_rows) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                const int co = coc * 64 + pc * 32 + c;
+                if (co < p.cout_real) atomicAdd(p.db + co, __uint_as_float(v[c]) * inv);
+              }
+            }
             if (g >= 0 && ci < p.cin_real) {
 #pragma unroll
               for (int c = 0; c < 32; ++c) {
@@ -360,6 +380,7 @@ int tg_wgrad_tcgen05(const tg_wgrad_desc* d, void* stream) {
   p.ci_chunks = d->cin / 64;
   p.co_chunks = d->cout / 64;
   p.dw = d->dw;
+  p.db = d->db;
   p.scale = d->scale;
   p.flags = 0;
   if (const char* e = getenv("TG_WGRAD_FLAGS")) p.flags = atoi(e);
@@ -371,10 +392,13 @@ int tg_wgrad_tcgen05(const tg_wgrad_desc* d, void* stream) {
   // one extra 1 KB of slack after the halo box: the unused half of the last tap pair reads one
   // pixel row past the box (ignored accumulator rows)
   p.stage_bytes = ((p.x_bytes + 1023u) & ~1023u) + (uint32_t)p.n_planes * kDzTileBytes;
-  int stages = (int)((kSmemLimit - 2048u) / p.stage_bytes);
+  const uint32_t ones_bytes = (conv && d->db) ? 3072u : 0u;       // 2560 used (two 8-row K groups one box row apart)
+  int stages = (int)((kSmemLimit - 2048u - ones_bytes) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   TG_REQUIRE(stages >= 2, TG_E_UNSUPPORTED, "wgrad_tcgen05: shared memory budget");
   p.n_stages = stages;
+  p.off_ones = 1024u + (uint32_t)stages * p.stage_bytes;
+  TG_REQUIRE(!(d->db && !conv), TG_E_UNSUPPORTED, "wgrad_tcgen05: fused bias gradient is for conv3x3 layers");
   // A and B both MN-major (bits 15, 16), fp16 inputs, fp32 accumulate, M = 128, N = 64
   p.idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 

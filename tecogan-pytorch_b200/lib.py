@@ -44,7 +44,7 @@ class ChainLayer(ctypes.Structure):
 class WgradDesc(ctypes.Structure):
     """struct tg_wgrad_desc"""
     _fields_ = [
-        ('x', c_void_p), ('dz', c_void_p), ('dw', c_void_p), ('scale', c_void_p),
+        ('x', c_void_p), ('dz', c_void_p), ('dw', c_void_p), ('scale', c_void_p), ('db', c_void_p),
         ('n', c_int32), ('h', c_int32), ('w', c_int32),
         ('cin', c_int32), ('cout', c_int32), ('cin_real', c_int32), ('cout_real', c_int32),
         ('kind', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),

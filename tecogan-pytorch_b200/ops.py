@@ -511,7 +511,7 @@ class PackedDgrad:
         return y
 
 
-def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0):
+def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0, db=None):
     """dw (fp32, the parameter's layout, pre-zeroed or accumulating) += 1/scale * x (*) dz for the
     forward layer `fwd` (PackedConv): x = its NHWC fp16 input, dz = gradient of its pre-activation
     output (NHWC fp16, pad64(cout_real) channels)."""
@@ -529,6 +529,13 @@ def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0):
     d = L.WgradDesc()
     d.x, d.dz, d.dw = x.data_ptr(), dz.data_ptr(), dw.data_ptr()
     d.scale = scale.ws.data_ptr() if scale is not None else None
+    fuse_db = db is not None and fwd.kind == L.CONV_3X3 and (impl or default_conv_impl()) == 'tcgen05'
+    if db is not None:
+        _req(db, torch.float32, 'db', 1)
+        if db.numel() != fwd.cout_real:
+            raise L.TecoganB200Error('wgrad: db must have cout_real elements')
+        if fuse_db:
+            d.db = db.data_ptr()            # bias gradient from the same MMAs
     d.n, d.h, d.w, d.cin, d.cout = n, h, w, cin, cout
     d.cin_real, d.cout_real, d.kind, d.max_ctas, d.reserved = fwd.cin_real, fwd.cout_real, fwd.kind, max_ctas, 0
     lib = L.load()
@@ -537,6 +544,8 @@ def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0):
         L.check(lib.tg_wgrad_tcgen05(ctypes.byref(d), _stream()), 'tg_wgrad_tcgen05')
     else:
         L.check(lib.tg_wgrad_simt(ctypes.byref(d), _stream()), 'tg_wgrad_simt')
+    if db is not None and not fuse_db:
+        bias_grad(dz, db, scale)            # transposed conv / cross-check path: separate reduction kernel
     return dw
 
 

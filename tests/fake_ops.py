@@ -153,7 +153,9 @@ def _s(scale):
 
 
 @torch.enable_grad()
-def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0):
+def wgrad(fwd, x, dz, dw, scale=None, impl=None, max_ctas=0, db=None):
+    if db is not None:
+        bias_grad(dz, db, scale)
     xin = to_nchw(x, fwd.cin_real).requires_grad_(False)
     g = to_nchw(dz, fwd.cout_real)
     w = torch.zeros_like(dw, requires_grad=True)

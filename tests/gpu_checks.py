@@ -793,6 +793,13 @@ def check_wgrad(kind=None, cin=64, cout=64, h=20, w=24, n=2, cin_real=None, cout
     torch.cuda.synchronize()
     out['bias_rel_l2'] = rell2(db.cpu().numpy(), f16(gy).sum((0, 2, 3)).numpy())
     assert out['bias_rel_l2'] <= 1e-4, out
+    # bias gradient fused into the wgrad launch (conv layers: the spare half of the last tap pair reads ones)
+    db2, dw2 = torch.zeros(cout_real, device=DEV), torch.zeros(wshape, device=DEV)
+    ops.wgrad(fwd, xg, dzg, dw2, db=db2)
+    torch.cuda.synchronize()
+    out['fused_bias_rel_l2'] = rell2(db2.cpu().numpy(), f16(gy).sum((0, 2, 3)).numpy())
+    out['fused_dw_rel_l2'] = rell2(dw2.cpu().numpy(), dw_ref.numpy())
+    assert out['fused_bias_rel_l2'] <= 1e-4 and out['fused_dw_rel_l2'] <= 1e-3, out
     return out
 
 

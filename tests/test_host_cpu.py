@@ -46,8 +46,8 @@ def test_conv_desc_struct_layout_matches_header():
     assert ctypes.sizeof(L.ConvDesc) == 5 * 8 + 12 * 4 + 8
     assert L.ConvDesc.n.offset == 40 and L.ConvDesc.max_ctas.offset == 40 + 10 * 4
     assert L.ConvDesc.mask.offset == 88
-    # struct tg_wgrad_desc: 4 pointers + 10 int32
-    assert ctypes.sizeof(L.WgradDesc) == 4 * 8 + 10 * 4 and L.WgradDesc.n.offset == 32
+    # struct tg_wgrad_desc: 5 pointers + 10 int32
+    assert ctypes.sizeof(L.WgradDesc) == 5 * 8 + 10 * 4 and L.WgradDesc.n.offset == 40
 
 
 def test_backward_entry_points_reject_bad_arguments_without_a_gpu():

@@ -490,15 +490,13 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
 #pragma unroll
         for (int i = 0; i < 8; i += 2) ld_global_256(rp + i, res[i], res[i + 1]);
       }
-      uint4 msk[BWD ? 8 : 1];
+      // derivative epilogue: the stored forward output whose sign gives act' -- fetched per 32-channel piece right
+      // before that piece's TMEM load (keeping all 128 bytes live across the accumulator wait spilled registers)
       const bool has_mask = BWD && kCanRes && d.act >= TG_ACT_DRELU && inb;
-      if (BWD && has_mask) {
-        const uint4* mp = reinterpret_cast<const uint4*>(
-            reinterpret_cast<const __half*>(d.mask) +
-            (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) ld_global_256(mp + i, msk[BWD ? i : 0], msk[BWD ? i + 1 : 0]);
-      }
+      const uint4* mp = nullptr;
+      if (BWD && has_mask)
+        mp = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(d.mask) +
+                                            (((size_t)tc.n * d.h + py) * d.w + px) * d.cout + tc.nb * p.bn);
       mbar_wait(bar_tfull + 8 * buf, bphase, 7);
       TG_ACC(te_tfull, t_s);
       t_s = TG_T0();
@@ -516,6 +514,11 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
 #pragma unroll
           for (int pc = 0; pc < 2; ++pc) {                // bn == 64: two 32-column pieces
             uint32_t v[32];
+            uint4 msk[BWD ? 4 : 1];
+            if (BWD && has_mask) {
+              ld_global_256(mp + pc * 4, msk[0], msk[BWD ? 1 : 0]);
+              ld_global_256(mp + pc * 4 + 2, msk[BWD ? 2 : 0], msk[BWD ? 3 : 0]);
+            }
             tmem_ld32(tmem_base + buf * acc_stride + acc * p.bn + pc * 32 + ((uint32_t)(q * 32) << 16), v);
             tmem_ld_wait();
             if (acc == acc_hi - 1 && pc == 1) {
@@ -551,7 +554,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
                     a0 += rf.x; a1 += rf.y;
                   }
                   if (has_mask) {
-                    const float2 mf = __half22float2(reinterpret_cast<const __half2*>(&msk[BWD ? pc * 4 + i : 0])[j]);
+                    const float2 mf = __half22float2(reinterpret_cast<const __half2*>(&msk[BWD ? i : 0])[j]);
                     a0 *= tg_dact(mf.x, d.act); a1 *= tg_dact(mf.y, d.act);
                   }
                 }

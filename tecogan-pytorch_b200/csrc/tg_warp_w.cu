@@ -54,10 +54,30 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
   constexpr int NF = LRFLOW ? (2 * FH * FW + 31) / 32 : 2 * S;     // prefetched flow values per lane
   constexpr int NL = (LRW * 3 + 31) / 32;                         // prefetched lr_curr values per lane
   float pf[NF], pl[NL];
-  auto prefetch = [&](long long u) {
-    const int xb = (int)(u % xblocks);
-    const int y = (int)((u / xblocks) % h);
-    const int nn = (int)(u / ((long long)xblocks * h));
+  // unit -> (image, LR row, column block), walked incrementally: no (64-bit) divisions per unit -- the kernel is
+  // close to issue-bound (~870 warp instructions per unit in the ncu capture), index arithmetic included
+  struct UnitPos { int nn, y, xb; };
+  const int step_x = (int)(wstride % xblocks), step_y = (int)(wstride / xblocks);
+  auto advance = [&](UnitPos& c) {
+    c.xb += step_x;
+    c.y += step_y;
+    if (c.xb >= xblocks) { c.xb -= xblocks; ++c.y; }
+    while (c.y >= h) { c.y -= h; ++c.nn; }
+  };
+  // lane-constant decompositions of the prefetch indices (hoisted out of the unit loop)
+  int f_col[NF], f_row[NF], f_comp[NF], l_k[NL], l_p[NL];
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+    const int i = lane + 32 * j;
+    f_col[j] = i % FW; f_row[j] = (i / FW) % FH; f_comp[j] = i / (FH * FW);
+  }
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    const int i = lane + 32 * j;
+    l_k[j] = i / LRW; l_p[j] = i - l_k[j] * LRW;
+  }
+  auto prefetch = [&](const UnitPos& c) {
+    const int xb = c.xb, y = c.y, nn = c.nn;
     const int x0 = xb * LRW;
     if (LRFLOW) {
       // hr_flow = S * upsample_func(reflect_pad(lr_flow))   (tecogan_nets.py:239-244)
@@ -66,10 +86,9 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
         const int i = lane + 32 * j;
         float v = 0.f;
         if (i < 2 * FH * FW) {
-          const int col = i % FW, row = (i / FW) % FH, comp = i / (FH * FW);
-          const int yy = tg_reflect_hi(tg_clampi(y - 1 + row, 0, h - 1), h8);
-          const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + col, 0, w - 1), w8);
-          v = __ldg(flow + (((size_t)nn * 2 + comp) * h8 + yy) * w8 + xx);
+          const int yy = tg_reflect_hi(tg_clampi(y - 1 + f_row[j], 0, h - 1), h8);
+          const int xx = tg_reflect_hi(tg_clampi(x0 - 1 + f_col[j], 0, w - 1), w8);
+          v = __ldg(flow + (((size_t)nn * 2 + f_comp[j]) * h8 + yy) * w8 + xx);
         }
         pf[j] = v;
       }
@@ -91,19 +110,19 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
     for (int j = 0; j < NL; ++j) {
       const int i = lane + 32 * j;
       float v = 0.f;
-      if (i < LRW * 3) {
-        const int k = i / LRW, p = i - k * LRW;
-        if (x0 + p < w) v = __ldg(lr_curr + (((size_t)nn * 3 + k) * h + y) * w + x0 + p);
-      }
+      if (i < LRW * 3 && x0 + l_p[j] < w) v = __ldg(lr_curr + (((size_t)nn * 3 + l_k[j]) * h + y) * w + x0 + l_p[j]);
       pl[j] = v;
     }
   };
   const long long u_first = (long long)blockIdx.x * kWarpsPerCta + warp;
-  if (u_first < units) prefetch(u_first);
-  for (long long u = u_first; u < units; u += wstride) {
-    const int xb = (int)(u % xblocks);
-    const int y = (int)((u / xblocks) % h);
-    const int nn = (int)(u / ((long long)xblocks * h));
+  UnitPos cur, nxt;
+  cur.xb = (int)(u_first % xblocks);
+  cur.y = (int)((u_first / xblocks) % h);
+  cur.nn = (int)(u_first / ((long long)xblocks * h));
+  nxt = cur;
+  if (u_first < units) prefetch(cur);
+  for (long long u = u_first; u < units; u += wstride, cur = nxt) {
+    const int xb = cur.xb, y = cur.y, nn = cur.nn;
     const int x0 = xb * LRW;
     const int X = x0 * S + lane;
     float uu[S], vv[S];
@@ -118,14 +137,11 @@ warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restr
     }
 #pragma unroll
     for (int j = 0; j < NL; ++j) {
-      const int i = lane + 32 * j;
-      if (i < LRW * 3) {
-        const int k = i / LRW, p = i - k * LRW;
-        tile[p * tstride + k] = __float2half(pl[j]);
-      }
+      if (lane + 32 * j < LRW * 3) tile[l_p[j] * tstride + l_k[j]] = __float2half(pl[j]);
     }
     // ... and start the next unit's reads before this unit's gathers
-    if (u + wstride < units) prefetch(u + wstride);
+    advance(nxt);
+    if (u + wstride < units) prefetch(nxt);
     if (LRFLOW) {
       __syncwarp();
       float kx[4], hx[2][FH];

@@ -65,6 +65,7 @@ struct ChainParams {
   int n_layers, n, h, w, tiles_x, tiles_y, num_tiles;
   uint32_t idesc;
   unsigned long long* dbg;         // optional per-CTA timers (same slots as tg_conv_tcgen05)
+  uint32_t xflags;                 // TIMING builds only: ablation switches (TG_CHAIN_ABLATE), results are then WRONG
 };
 
 __device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p) {
@@ -138,6 +139,9 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   uint8_t* sm = smem_raw + (base - raw);
   constexpr bool timing = TIMING;
   const long long t_kernel0 = timing ? clock64() : 0;
+  // ablation switches of the TIMING build (tools/conv_timers.py chain-ablate): 1 no dependency waits, 2 no epilogue
+  // global loads/stores, 4 no flag publication, 8 no TMA loads, 16 one MMA per tile, 32 no bias reads
+  const uint32_t xf = timing ? cp.xflags : 0u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = base;                 // [kStages <= 8]
@@ -209,7 +213,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         const int n = tile / per_img;
         const int r = tile - n * per_img;
         const int ty = r / cp.tiles_x, tx = r - ty * cp.tiles_x;
-        if (l > 0) {
+        if (l > 0 && !(xf & 1u)) {
           // the dependency checker (warp 3) has verified the halo tiles of every tile up to *deps_ok
           const long long t0 = timing ? clock64() : 0;
           const uint32_t seq = (uint32_t)(l * n_my + k);
@@ -231,8 +235,12 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
           const long long t0 = timing ? clock64() : 0;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
           if (timing) tw_empty += clock64() - t0;
-          mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
-          tma_load_4d(smem_stage0 + stage * kStageBytes, map, bar_full + 8 * stage, 0, tx * TW - 1, ty * TH - 1, n);
+          if (xf & 8u) {
+            mbar_expect_tx(bar_full + 8 * stage, 0);
+          } else {
+            mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
+            tma_load_4d(smem_stage0 + stage * kStageBytes, map, bar_full + 8 * stage, 0, tx * TW - 1, ty * TH - 1, n);
+          }
           CT_TRACE(l * n_my + k, 5);
         }
         __syncwarp();
@@ -298,6 +306,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
 #pragma unroll
           for (int i = (part == 0 ? 0 : 16); i < (part == 0 ? 16 : 36); ++i) {
             const int tap = i >> 2, kk = i & 3;
+            if ((xf & 16u) && i > 0) continue;
             const uint32_t off = (uint32_t)((tap / 3) * BOXW + tap % 3) * 8u;   // (dy+1, dx+1) pixels, 128 B each
             int slot = slot0 + tap;
             if (slot >= kSlots) slot -= kSlots;
@@ -403,7 +412,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     for (int rr = 0; rr < R; ++rr) { q[rr] = n_my + rr * 3 + (sub < 3 ? sub : 0); setup(rr); }
     int head = n_my;                                    // first tile of the sequence not yet verified
     long long t_s = clock64();
-    while (head < total) {
+    while (head < total && !(xf & 1u)) {
       uint32_t v[R], m[R];
 #pragma unroll
       for (int rr = 0; rr < R; ++rr) v[rr] = ok[rr] ? 0u : ld_relaxed_gpu(f[rr]);   // independent: latencies overlap
@@ -475,7 +484,7 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       const size_t pix = ((size_t)n * cp.h + py) * cp.w + px;
       const float slope = tg_act_slope(ly.act);
       uint4 res[8];
-      const bool has_res = ly.res != nullptr && inb;
+      const bool has_res = ly.res != nullptr && inb && !(xf & 2u);
       if (has_res) {
         const uint4* rp = reinterpret_cast<const uint4*>(ly.res + pix * 64);
 #pragma unroll
@@ -511,7 +520,8 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         for (int i = 0; i < 4; ++i) {
           __half2* o = reinterpret_cast<__half2*>(&ov[i]);
           const __half2* rh = reinterpret_cast<const __half2*>(&res[pc * 4 + i]);
-          const float4 b0 = bias4[i * 2], b1 = bias4[i * 2 + 1];
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (!(xf & 32u)) { b0 = bias4[i * 2]; b1 = bias4[i * 2 + 1]; }
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -531,13 +541,13 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
           if (gtid == 0) { fence_acq_rel_gpu(); st_relaxed_gpu(pend_flag, pend_val); CT_TRACE(pend_seq, 3); }
           pending = false;
         }
-        if (inb) {
+        if (inb && !(xf & 2u)) {
           st_global_256(orow + pc * 4, ov[0], ov[1]);
           st_global_256(orow + pc * 4 + 2, ov[2], ov[3]);
         }
       }
       if (gtid == 0) CT_TRACE(g, 2);
-      if (l + 1 < L) {
+      if (l + 1 < L && !(xf & 4u)) {
         pending = true;
         pend_flag = flags + tile;
         pend_val = fbase + (uint32_t)l + 1u;
@@ -617,6 +627,11 @@ int tg_conv_chain_tcgen05(const tg_chain_layer* layers, int n_layers, int n, int
   p.sync = reinterpret_cast<uint32_t*>(sync_ws);
   p.idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.dbg = tg_conv_timer_buffer();
+  p.xflags = 0;
+  if (p.dbg != nullptr) {
+    const char* e = getenv("TG_CHAIN_ABLATE");
+    if (e != nullptr) p.xflags = (uint32_t)atoi(e);
+  }
 
   const void* bufs[kMaxMaps];
   int n_maps = 0;

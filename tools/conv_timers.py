@@ -122,6 +122,48 @@ def run_chain(blocks=10, n=4, h=134, w=320):
     return out
 
 
+def run_chain_ablate(n=4, h=134, w=320, blocks=10, max_ctas=0):
+    """TIMING build of the chain with parts switched off (TG_CHAIN_ABLATE bits: 1 no dependency waits, 2 no epilogue
+    global loads/stores, 4 no flag publication, 8 no TMA loads, 16 one MMA per tile, 32 no bias reads) -- the
+    results are wrong on purpose; only the per-tile period is read."""
+    dev = 'cuda:0'
+    nl = 1 + 2 * blocks
+    pcs = [ops.PackedConv(torch.randn(64, 64, 3, 3, device=dev) * 0.04, torch.zeros(64, device=dev), L.CONV_3X3,
+                          L.ACT_RELU if (i == 0 or i % 2 == 1) else L.ACT_NONE) for i in range(nl)]
+    specs = [(pcs[0], 0, 1, None)]
+    for b in range(blocks):
+        specs += [(pcs[1 + 2 * b], 1, 2, None), (pcs[2 + 2 * b], 2, 1, 1)]
+    chain = ops.ConvChain(specs)
+    x = torch.randn(n, h, w, 64, device=dev).half()
+    bufs = [x, torch.empty_like(x), torch.empty_like(x)]
+    for _ in range(3):
+        chain(bufs)
+    lib = L.load()
+    buf = torch.zeros(148 * 16 + 8 * 24 * 16, dtype=torch.int64, device=dev)
+    combos = [0, 1, 5, 2, 3, 7, 7 + 32, 8 + 7, 16, 16 + 7, 16 + 15, 16 + 15 + 32, 8, 32]
+    for fl in combos:
+        os.environ['TG_CHAIN_ABLATE'] = str(fl)
+        buf.zero_()
+        lib.tg_debug_set_conv_timers(ctypes.c_void_p(buf.data_ptr()))
+        us = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            chain(bufs)
+            e1.record()
+            torch.cuda.synchronize()
+            us.append(e0.elapsed_time(e1) * 1e3)
+        lib.tg_debug_set_conv_timers(ctypes.c_void_p(0))
+        t = buf[:148 * 16].view(148, 16).cpu().double()
+        t = t[t[:, 6] > 0]
+        tiles = t[:, 7].max().item()
+        out = {'ablate': fl, 'us': round(min(us), 1), 'tile_layers_max': tiles,
+               'kernel_cycles_per_tile': round(t[:, 6].max().item() / max(tiles, 1)),
+               'per_tile': {nm: round(t[:, i].mean().item() / max(t[:, 7].mean().item(), 1)) for i, nm in enumerate(CHAIN_NAMES) if nm != 'tiles'}}
+        print(json.dumps(out), flush=True)
+    os.environ.pop('TG_CHAIN_ABLATE', None)
+
+
 TAIL_NAMES = ['mma_wait_full', 'mma_wait_tempty', 'mma_wait_hrfull', 'mma_wait_d2empty', 'mma_total', 'epiA_wait',
               'epiA_busy', 'epiB_wait', 'epiB_tmem', 'epiB_exchange', 'epiB_residual', 'epiB_store', 'epiB_total',
               'kernel', 'tiles']
@@ -172,6 +214,9 @@ if __name__ == '__main__':
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'chain':
         run_chain()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'chain-ablate':
+        run_chain_ablate()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'pair':
         for flags in ('0', '16'):

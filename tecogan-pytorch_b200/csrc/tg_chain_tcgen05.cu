@@ -4,11 +4,9 @@
 //   tiles   : 16x8 output pixels (M = 128), static assignment tile = cta + k*grid for every layer
 //   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 4 stages; the nine
 //             taps are nine shifted UMMA-descriptor views of the box (see tg_conv_tcgen05.cu)
-//   B       : packed weights resident in smem in a ring of 14 tap slots (tap t of layer l in slot
-//             (9l + t) % 14): the next layer's taps 0-4 stream in while the current layer computes,
-//             taps 5-8 reuse the slots that the LAST tile of the current layer hands back (a
-//             tcgen05.commit behind its taps 0-3) -- no weight-reload bubble at layer boundaries and
-//             40 KB less shared memory than a double buffer (4 A stages instead of 3)
+//   B       : packed weights double-buffered in smem (layer l in buffer l & 1, 72 KB each): layer l+1
+//             streams in (one bulk copy) as soon as both MMA issuers have retired layer l-1 -- a whole
+//             layer ahead of its first use, so there is no reload bubble at layer boundaries
 //   D       : one 64-column fp32 accumulator per tile, 8 tiles in flight in TMEM (splitting the taps
 //             over two partial accumulators was measured: no gain).
 //   layers  : a tile of layer l needs the tiles of layer l-1 under its halo.  Epilogue groups
@@ -16,8 +14,15 @@
 //             checker warp polls the <= 9 flags of each of the next nine tiles (sliding window)
 //             ahead of the TMA producer and hands it an in-order "verified" counter.  No launch,
 //             pipeline fill/drain, weight reload bubble or grid barrier between layers.
-//   roles   : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator + weight streamer,
-//             warp 3 dependency checker, warps 4..11 two epilogue groups alternating tiles.
+//   roles   : warp 0 TMA producer, warps 1 and 12 MMA issuers (even / odd tiles of the CTA's sequence),
+//             warp 2 TMEM allocator + weight streamer, warp 3 dependency checker, warps 4..11 two
+//             epilogue groups alternating tiles.
+//             TWO issuers because an N=64 MMA occupies the tensor pipe for 48 cycles and the pipe hides
+//             only ~180 cycles without a new instruction: one warp needs ~80 cycles per MMA for the issue
+//             plus its bookkeeping (barrier polls, commits, descriptor arithmetic), so with one issuer
+//             the pipe idles 40 % of the time; two warps' instruction streams interleave in the pipe and
+//             it stays fed (tools/mma_probe.cu: 97 -> 52 cycles per MMA with 40 cycles of other work
+//             per MMA and issuer).
 //
 // Replaces the 21 nn.Conv2d launches of SRNet.conv_in / ResidualBlock (tecogan_nets.py:92-100,
 // 111-116, 139-141) per step.
@@ -33,10 +38,11 @@
 namespace {
 
 constexpr int TH = 16, TW = 8, BOXW = TW + 2, BOXH = TH + 2;
-constexpr int kThreads = 384;
+constexpr int kThreads = 416;                           // 13 warps, see `roles`
+constexpr int kIssuerBWarp = 12;
 constexpr int kMaxMaps = 4;
-constexpr int kStages = 4;
-constexpr int kSlots = 14;                              // weight ring: tap t of layer l lives in slot (9l + t) % kSlots
+constexpr int kStages = 3;
+constexpr int kSlots = 18;                              // two weight buffers of nine taps: layer l in buffer l & 1
 constexpr int kBufs = 8;                               // tiles in flight in TMEM (8 x 64 columns)
 constexpr uint32_t kAccStride = 64;
 constexpr uint32_t kTmemCols = 512;
@@ -124,7 +130,7 @@ __device__ __forceinline__ void ld_global_256_l2(const void* ptr, uint4& a, uint
 }
 
 enum { CT_PROD_FLAGS = 0, CT_PROD_EMPTY, CT_MMA_TOTAL, CT_MMA_WAIT, CT_EPI_TFULL, CT_EPI_TOTAL, CT_KERNEL, CT_TILES,
-       CT_MMA_ISSUE0, CT_MMA_LOOK, CT_MMA_ISSUE1, CT_MMA_BOUNDARY,
+       CT_MMA_ISSUE0, CT_MMA_LOOK, CT_MMA_ISSUE1, CT_MMA_BOUNDARY, CT_CHK_ITERS, CT_CHK_FENCE, CT_CHK_HITS, CT_CHK_TOTAL,
        CT_SLOTS = 16 };
 
 // event trace of CTA 0 (TIMING builds): trace[seq * 8 + event] = clock64, behind the 148 x 16 timer slots
@@ -143,15 +149,18 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   // global loads/stores, 4 no flag publication, 8 no TMA loads, 16 one MMA per tile, 32 no bias reads
   const uint32_t xf = timing ? cp.xflags : 0u;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = base;                 // [kStages <= 8]
+  // warp index through a shuffle broadcast: the compiler then KNOWS it is warp-uniform and keeps the role
+  // loops' counters, barrier addresses and UMMA descriptors in uniform registers (a plain threadIdx.x >> 5
+  // leaves them in vector registers and pays an R2UR per descriptor word in front of every MMA)
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t bar_full = base;                 // [2 issuers][kStages]: per ISSUER -- with an odd stage count an issuer meets
+                                                  // a stage only every other time it is filled, and a parity wait must see
+                                                  // every completion of its barrier (tests/test_chain_protocol_model.py, bug 4)
   const uint32_t bar_empty = base + 64;           // [kStages <= 8]
   const uint32_t bar_tfull = base + 128;          // [kBufs]
   const uint32_t bar_tempty = base + 192;         // [kBufs]
-  const uint32_t bar_wfull = base + 256;          // [9] tap t of the current layer's weights landed
-  const uint32_t bar_wfree = base + 336;          // [9] every MMA of the layer that reads tap t retired
-  const uint32_t bar_wstart = base + 416;         // [1] the MMA issuer has taken delivery of a layer's weights
-  const uint32_t bar_wearly = base + 424;         // [1] the streamer is past its waits for the next layer's early taps
+  const uint32_t bar_wfull = base + 256;          // [2] the weights of a layer have landed in buffer l & 1
+  const uint32_t bar_wfree = base + 272;          // [2] both issuers' MMAs of the layer in buffer l & 1 have retired
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 432);
   volatile uint32_t* epoch_s = reinterpret_cast<volatile uint32_t*>(sm + 436);
   const uint32_t deps_ok_addr = base + 440;       // tiles (in this CTA's sequence) whose dependencies are verified
@@ -170,11 +179,10 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     for (int i = 0; i < kMaxMaps; ++i) tma_prefetch_desc(&cp.maps[i]);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < 2 * kStages; ++s) mbar_init(bar_full + 8 * s, 1);
     for (int i = 0; i < kBufs; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
-    for (int i = 0; i < 9; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 1); }
-    mbar_init(bar_wstart, 1);
-    mbar_init(bar_wearly, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_wfull + 8 * i, 1); mbar_init(bar_wfree + 8 * i, 2); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), kTmemCols);
@@ -184,11 +192,11 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
   const uint32_t tmem_base = *tmem_ptr_s;
 
   // Weights are static across the step (packed at module init / refresh, never by the predecessor
-  // kernel): layer 0's are requested, tap by tap, before joining the PDL wait.
+  // kernel): the first two layers' are requested before joining the PDL wait.
   if (warp == 2 && lane == 0) {
-    for (int t = 0; t < 9; ++t) {
-      mbar_expect_tx(bar_wfull + 8 * t, kTapWBytes);
-      bulk_load(smem_w0 + t * kTapWBytes, cp.layers[0].w + (size_t)t * kTapWBytes, kTapWBytes, bar_wfull + 8 * t);
+    for (int l = 0; l < 2 && l < L; ++l) {
+      mbar_expect_tx(bar_wfull + 8 * l, 9 * kTapWBytes);
+      bulk_load(smem_w0 + (uint32_t)l * 9u * kTapWBytes, cp.layers[l].w, 9 * kTapWBytes, bar_wfull + 8 * l);
     }
   }
   tg_pdl_wait();
@@ -235,11 +243,12 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
           const long long t0 = timing ? clock64() : 0;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
           if (timing) tw_empty += clock64() - t0;
+          const uint32_t fb = bar_full + 8 * (((l * n_my + k) & 1) * kStages + stage);   // the consuming issuer's barrier
           if (xf & 8u) {
-            mbar_expect_tx(bar_full + 8 * stage, 0);
+            mbar_expect_tx(fb, 0);
           } else {
-            mbar_expect_tx(bar_full + 8 * stage, kHaloBytes);
-            tma_load_4d(smem_stage0 + stage * kStageBytes, map, bar_full + 8 * stage, 0, tx * TW - 1, ty * TH - 1, n);
+            mbar_expect_tx(fb, kHaloBytes);
+            tma_load_4d(smem_stage0 + stage * kStageBytes, map, fb, 0, tx * TW - 1, ty * TH - 1, n);
           }
           CT_TRACE(l * n_my + k, 5);
         }
@@ -251,102 +260,111 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
       cp.dbg[b * CT_SLOTS + CT_PROD_FLAGS] = tw_flags;
       cp.dbg[b * CT_SLOTS + CT_PROD_EMPTY] = tw_empty;
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
-    int stage = 0, buf = 0, l = 0, k = 0;
-    uint32_t phase = 0, bphase = 0;
-    const uint64_t a_hi = make_sdesc(0, (uint32_t)BOXW * 128u);   // 8-row groups = consecutive tile rows
-    const uint64_t b_hi = make_sdesc(0, 1024u);
-    const long long t_mma0 = timing ? clock64() : 0;
+  } else if (warp == 1 || warp == kIssuerBWarp) {
+    // ============================================================ MMA issuers
+    // Issuer w (0: warp 1, 1: warp 12) owns the tiles g = w, w + 2, ... of the CTA's sequence; A stage
+    // g % kStages, accumulator g % kBufs.  All 32 lanes run the loop on warp-uniform values (uniform
+    // datapath: one add per descriptor), one elected lane issues.  Per layer and issuer: ENTER = wait for
+    // the layer's weights, EXIT = commit behind the issuer's last tile of the layer onto wfree[l & 1]
+    // (count 2: the buffer is refilled when BOTH issuers' MMAs of the layer have retired).  An issuer
+    // with no tile in a layer (one tile per CTA and layer) enters and exits it all the same, in order,
+    // so every parity wait below stays at most one phase behind its barrier.
+    const int w = warp == 1 ? 0 : 1;
+    const uint32_t a_hi32 = (uint32_t)(make_sdesc(0, (uint32_t)BOXW * 128u) >> 32);   // 8-row groups = consecutive tile rows
+    const uint32_t b_hi32 = (uint32_t)(make_sdesc(0, 1024u) >> 32);
+    // descriptor low words carry the LBO field (1 << 16) beside the address: one add per operand
+    const uint32_t a_lo0 = ((smem_stage0 & 0x3FFFFu) >> 4) + 0x10000u;
+    const uint32_t b_lo0 = ((smem_w0 & 0x3FFFFu) >> 4) + 0x10000u;
+    const bool tm = timing && w == 0;
+    const long long t_mma0 = tm ? clock64() : 0;
     long long tw = 0, t_i0 = 0, t_lk = 0, t_i1 = 0, t_bd = 0;
-    mbar_wait(bar_tempty, 1, 4);                 // fresh barrier: passes immediately
-    mbar_wait(bar_full, 0, 5);
-    tc_fence_after();
-    const uint32_t wb16 = (smem_w0 & 0x3FFFFu) >> 4;
-    for (int g = 0; g < total; ++g) {
-      const bool first_k = k == 0;
-      const bool last_k = k == n_my - 1;
-      const bool hand_over = last_k && l + 1 < L;      // weight slots go back to the streamer tap by tap
-      const bool has_next = g + 1 < total;
-      const int nstage = (stage + 1 == kStages) ? 0 : stage + 1;
-      const uint32_t nphase = (stage + 1 == kStages) ? (phase ^ 1u) : phase;
-      const int nbuf = (buf + 1 == kBufs) ? 0 : buf + 1;
-      const uint32_t nbphase = (buf + 1 == kBufs) ? (bphase ^ 1u) : bphase;
-      const uint32_t sa16 = ((smem_stage0 + stage * kStageBytes) & 0x3FFFFu) >> 4;
+    int g = w, l = 0, k = w, entered = -1;
+    while (k >= n_my) { k -= n_my; ++l; }
+    // A stage g % kStages; its 'landed' barrier full[w][stage] completes once per 2 * kStages tiles (kStages is odd)
+    static_assert(kStages % 2 == 1, "phase of full[w][stage] below assumes an odd stage count");
+    const uint32_t my_full = bar_full + 8 * (w * kStages);
+    int stage = w % kStages, buf = w, fuse = 0;     // fuse: g / (2 kStages) = fills of (w, stage) so far, advanced with g
+    int fcnt = w;                                   // g % (2 kStages)
+    uint32_t bphase = 0;
+    if (g < total) {
+      mbar_wait(bar_tempty + 8 * buf, 1, 4);     // fresh barrier: passes immediately
+      mbar_wait(my_full + 8 * stage, 0, 5);
+      tc_fence_after();
+    }
+    for (; g < total; g += 2) {
+      // position of this issuer's next tile
+      int nk = k + 2, nl = l;
+      while (nk >= n_my) { nk -= n_my; ++nl; }
+      const bool has_next = g + 2 < total;
+      const bool last_mine = nl != l;                  // my last tile of layer l
+      int nstage = stage + 2;
+      if (nstage >= kStages) nstage -= kStages;
+      int nfcnt = fcnt + 2, nfuse = fuse;
+      if (nfcnt >= 2 * kStages) { nfcnt -= 2 * kStages; ++nfuse; }
+      const uint32_t nphase = (uint32_t)nfuse & 1u;
+      int nbuf = buf + 2; uint32_t nbphase = bphase;
+      if (nbuf >= kBufs) { nbuf -= kBufs; nbphase ^= 1u; }
+      const uint32_t sa = a_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+      const uint32_t sb = b_lo0 + (uint32_t)(l & 1) * (9u * (kTapWBytes >> 4));
       const uint32_t d0 = tmem_base + (uint32_t)buf * kAccStride;
-      const int slot0 = (9 * l) % kSlots;              // ring slot of this layer's tap 0
       bool next_ready = false;
       if (lane == 0) CT_TRACE(g, 6);
-      if (first_k) {
-        // first tile of a layer: its weights were streamed in behind the previous layer (normally
-        // all nine taps have landed long ago)
-        const long long tb0 = timing ? clock64() : 0;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) mbar_wait(bar_wfull + 8 * tap, (uint32_t)l & 1u, 3);
+      if (entered < l) {
+        const long long tb0 = tm ? clock64() : 0;
+        while (entered < l) {
+          ++entered;
+          mbar_wait(bar_wfull + 8 * (entered & 1), (uint32_t)(entered >> 1) & 1u, 3);
+          if (entered < l) {                           // a layer without a tile of mine: nothing to retire
+            if (elect_one_sync()) mbar_arrive(bar_wfree + 8 * (entered & 1));
+            __syncwarp();
+          }
+        }
         tc_fence_after();
-        // only now may the streamer complete the NEXT phase of the wfull barriers (a parity wait is
-        // sound only while the waiter is at most one phase behind)
-        if (lane == 0) mbar_arrive(bar_wstart);
-        __syncwarp();
-        if (timing) t_bd += clock64() - tb0;
+        if (tm) t_bd += clock64() - tb0;
       }
-      if (hand_over) {
-        // This tile completes the hand-over barriers of layer l.  The streamer waits on the PREVIOUS
-        // completion of wfree[4..8] (for the next layer's taps 0-4, which reuse layer l-1's slots): it
-        // must be past those waits first, or a late streamer would find the barriers two phases ahead
-        // (found by tests/test_chain_protocol_model.py; needs one tile per CTA and layer to happen).
-        mbar_wait(bar_wearly, (uint32_t)l & 1u, 10);
-      }
-      // The 36 MMAs are issued in two parts (taps 0-3 | taps 4-8).  On the last tile of a layer a
-      // commit behind each part hands those taps' ring slots back to the weight streamer.
+      // The 36 MMAs are issued in two parts (taps 0-3 | taps 4-8) with the look-ahead poll between them.
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
-        const long long tp0 = timing ? clock64() : 0;
+        const long long tp0 = tm ? clock64() : 0;
         if (elect_one_sync()) {
 #pragma unroll
           for (int i = (part == 0 ? 0 : 16); i < (part == 0 ? 16 : 36); ++i) {
             const int tap = i >> 2, kk = i & 3;
             if ((xf & 16u) && i > 0) continue;
             const uint32_t off = (uint32_t)((tap / 3) * BOXW + tap % 3) * 8u;   // (dy+1, dx+1) pixels, 128 B each
-            int slot = slot0 + tap;
-            if (slot >= kSlots) slot -= kSlots;
-            umma_f16(d0, a_hi | (uint64_t)(sa16 + off + 2u * kk),
-                     b_hi | (uint64_t)(wb16 + (uint32_t)slot * (kTapWBytes >> 4) + 2u * kk), cp.idesc, i >= 1 ? 1u : 0u);
-          }
-          if (hand_over) {
-#pragma unroll
-            for (int tap = (part == 0 ? 0 : 4); tap < (part == 0 ? 4 : 9); ++tap) umma_commit(bar_wfree + 8 * tap);
+            umma_f16_words(d0, sa + off + 2u * kk, a_hi32, sb + (uint32_t)tap * (kTapWBytes >> 4) + 2u * kk, b_hi32,
+                           cp.idesc, i >= 1 ? 1u : 0u);
           }
           if (part == 1) {
             umma_commit(bar_empty + 8 * stage);
             umma_commit(bar_tfull + 8 * buf);
+            if (last_mine) umma_commit(bar_wfree + 8 * (l & 1));
           }
         }
         __syncwarp();
-        if (timing) { if (part == 0) t_i0 += clock64() - tp0; else t_i1 += clock64() - tp0; }
-        const long long tl0 = timing ? clock64() : 0;
+        if (tm) { if (part == 0) t_i0 += clock64() - tp0; else t_i1 += clock64() - tp0; }
+        const long long tl0 = tm ? clock64() : 0;
         if (part == 0 && has_next) {
           // look ahead while MMAs are queued in the tensor pipe -- but never BLOCK before this tile
           // is committed: the next tile may (transitively) depend on this one through the flags
           // (test_wait: try_wait may suspend the warp for hundreds of cycles)
           uint32_t r = mbar_test_wait(bar_tempty + 8 * nbuf, nbphase ^ 1);
-          r &= mbar_test_wait(bar_full + 8 * nstage, nphase);
+          r &= mbar_test_wait(my_full + 8 * nstage, nphase);
           next_ready = __all_sync(0xFFFFFFFFu, r != 0);
           if (next_ready) tc_fence_after();
-          if (timing) t_lk += clock64() - tl0;
+          if (tm) t_lk += clock64() - tl0;
         }
       }
       if (has_next && !next_ready) {
-        const long long t0 = timing ? clock64() : 0;
+        const long long t0 = tm ? clock64() : 0;
         mbar_wait(bar_tempty + 8 * nbuf, nbphase ^ 1, 4);
-        mbar_wait(bar_full + 8 * nstage, nphase, 5);
-        if (timing) tw += clock64() - t0;
+        mbar_wait(my_full + 8 * nstage, nphase, 5);
+        if (tm) tw += clock64() - t0;
         tc_fence_after();
       }
-      stage = nstage; phase = nphase; buf = nbuf; bphase = nbphase;
-      if (last_k) { k = 0; ++l; } else { ++k; }
+      stage = nstage; fcnt = nfcnt; fuse = nfuse; buf = nbuf; bphase = nbphase; k = nk; l = nl;
     }
-    if (timing && lane == 0) {
+    if (tm && lane == 0) {
       cp.dbg[b * CT_SLOTS + CT_MMA_TOTAL] = clock64() - t_mma0;
       cp.dbg[b * CT_SLOTS + CT_MMA_WAIT] = tw;
       cp.dbg[b * CT_SLOTS + CT_TILES] = total;
@@ -357,96 +375,89 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
     }
   } else if (warp == 2) {
     // ============================================================ weight streamer
-    // Weights live in a ring of kSlots tap slots (tap t of layer l in slot (9l + t) % kSlots).  The
-    // next layer's first kSlots - 9 taps stream in while the current layer computes; its remaining
-    // taps reuse the slots the LAST tile of the current layer hands back after its first taps, so
-    // they land before the next layer's first tile gets to them: no reload bubble, and 40 KB less
-    // shared memory than a double buffer (one more A stage).
+    // Layer l lives in buffer l & 1.  It may be (re)filled once both issuers have retired layer l - 2
+    // (wfree[l & 1], one completion per use of the buffer): a whole layer before its first MMA.
     if (lane == 0) {
-      for (int l = 1; l < L; ++l) {
-        mbar_wait(bar_wstart, (uint32_t)(l - 1) & 1u, 9);   // layer l-1's weights have been taken over
-        for (int t = 0; t < 9; ++t) {
-          const int gi = 9 * l + t;                     // global tap index; its slot's previous tenant is gi - kSlots
-          if (gi >= kSlots) {
-            const int pl = (gi - kSlots) / 9, pt = (gi - kSlots) - pl * 9;
-            mbar_wait(bar_wfree + 8 * pt, (uint32_t)pl & 1u, 8);
-          }
-          mbar_expect_tx(bar_wfull + 8 * t, kTapWBytes);
-          bulk_load(smem_w0 + (uint32_t)(gi % kSlots) * kTapWBytes, cp.layers[l].w + (size_t)t * kTapWBytes,
-                    kTapWBytes, bar_wfull + 8 * t);
-          if (t == kSlots - 9 - 1) mbar_arrive(bar_wearly);   // every wait that refers to layer l-2 is behind us
-        }
+      for (int l = 2; l < L; ++l) {
+        mbar_wait(bar_wfree + 8 * (l & 1), (uint32_t)((l - 2) >> 1) & 1u, 8);
+        mbar_expect_tx(bar_wfull + 8 * (l & 1), 9 * kTapWBytes);
+        bulk_load(smem_w0 + (uint32_t)(l & 1) * 9u * kTapWBytes, cp.layers[l].w, 9 * kTapWBytes, bar_wfull + 8 * (l & 1));
       }
     }
   } else if (warp == 3) {
     // ============================================================ dependency checker
-    // Runs ahead of the TMA producer over a sliding window of 9 upcoming tiles of this CTA's
-    // sequence: tile q is watched by slot ((q - n_my) / 3) % 3 of the nine lanes (q - n_my) % 3,
-    // one lane per tile under its halo, polling that tile's progress flag (relaxed loads whose L2
-    // round trips overlap, one acquire fence per publication).  The in-order prefix of verified tiles is published
-    // through a shared-memory counter and the window slides on.
-    constexpr int R = 3, W = 3 * R;
+    // Runs ahead of the TMA producer over a sliding window of the next THREE tiles of this CTA's sequence:
+    // tile q is watched by the nine lanes 9 * ((q - n_my) % 3) .. + 8, one lane per tile under its halo, ONE
+    // relaxed gpu-scope load per lane and round (strong loads of one thread do not overlap: with three per lane
+    // a round took ~2000 cycles, all of it latency in the dependency loop between CTAs), one acquire fence per
+    // publication.  The in-order prefix of verified tiles is published through a shared-memory counter and the
+    // window slides on.
+    constexpr int W = 3;
     const int sub = lane / 9, nbr = lane - sub * 9;
-    int q[R] = {0, 0, 0};
-    const uint32_t* f[R];
-    uint32_t need[R];
-    bool ok[R];
-    auto setup = [&](int rr) {
-      f[rr] = nullptr;
-      need[rr] = 0;
-      if (sub < 3 && q[rr] < total) {
-        const int l = q[rr] / n_my, k = q[rr] - l * n_my;
+    int q = n_my + (sub < W ? sub : 0);
+    const uint32_t* f = nullptr;
+    uint32_t need = 0;
+    bool ok = true;
+    auto setup = [&]() {
+      f = nullptr;
+      need = 0;
+      if (sub < W && q < total) {
+        const int l = q / n_my, k = q - l * n_my;
         const int tile = b + k * G;
         const int n = tile / per_img;
         const int r = tile - n * per_img;
         const int ty = r / cp.tiles_x, tx = r - ty * cp.tiles_x;
         const int yy = ty + nbr / 3 - 1, xx = tx + nbr % 3 - 1;
         if (yy >= 0 && yy < cp.tiles_y && xx >= 0 && xx < cp.tiles_x) {
-          f[rr] = flags + (size_t)n * per_img + yy * cp.tiles_x + xx;
-          need[rr] = fbase + (uint32_t)l;               // flag >= need  <=>  layer l-1 of that tile is published
+          f = flags + (size_t)n * per_img + yy * cp.tiles_x + xx;
+          need = fbase + (uint32_t)l;                   // flag >= need  <=>  layer l-1 of that tile is published
         }
       }
-      ok[rr] = f[rr] == nullptr;
+      ok = f == nullptr;
     };
-#pragma unroll
-    for (int rr = 0; rr < R; ++rr) { q[rr] = n_my + rr * 3 + (sub < 3 ? sub : 0); setup(rr); }
+    setup();
     int head = n_my;                                    // first tile of the sequence not yet verified
     long long t_s = clock64();
+    long long c_iters = 0, c_fence = 0, c_hits = 0;
+    const long long c_t0 = timing ? clock64() : 0;
     while (head < total && !(xf & 1u)) {
-      uint32_t v[R], m[R];
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) v[rr] = ok[rr] ? 0u : ld_relaxed_gpu(f[rr]);   // independent: latencies overlap
-#pragma unroll
-      for (int rr = 0; rr < R; ++rr) {
-        if (!ok[rr]) ok[rr] = (int)(v[rr] - need[rr]) >= 0;
-        m[rr] = __ballot_sync(0xFFFFFFFFu, ok[rr]);
-      }
+      if (timing) ++c_iters;
+      if (!ok) ok = (int)(ld_relaxed_gpu(f) - need) >= 0;
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, ok);
       int p = 0;
       while (p < W && head + p < total) {
-        const int rel = head + p - n_my;
-        const int slot = (rel / 3) % R, sb = rel % 3;
-        const uint32_t mm = slot == 0 ? m[0] : (slot == 1 ? m[1] : m[2]);
-        if (((mm >> (9 * sb)) & 0x1FFu) != 0x1FFu) break;
+        const int grp = (head + p - n_my) % W;
+        if (((m >> (9 * grp)) & 0x1FFu) != 0x1FFu) break;
         ++p;
       }
       if (p > 0) {
-        fence_acq_rel_gpu();                            // relaxed polls + fence = acquire (every lane)
+        const long long tf0 = timing ? clock64() : 0;
+        if (!(xf & 64u)) fence_acq_rel_gpu();           // relaxed polls + fence = acquire (every lane)
+        if (timing) { c_fence += clock64() - tf0; c_hits += p; }
         __syncwarp();                                   // the other lanes' acquires happen-before the publication
         if (lane == 0) {
           st_release_cta_shared(deps_ok_addr, (uint32_t)(head + p));
           for (int i = 0; i < p; ++i) CT_TRACE(head + i, 4);
         }
         head += p;
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr)
-          if (q[rr] < head) { q[rr] += W; setup(rr); }
+        if (sub < W) {
+          bool moved = false;
+          while (q < head) { q += W; moved = true; }
+          if (moved) setup();
+        }
         t_s = clock64();
       } else if (clock64() - t_s > 3000000000LL) {
         if (b < 2 && lane == 0) printf("tg_conv_chain: flag timeout block=%d seq=%d of %d\n", b, head, total);
         __trap();
       }
     }
-  } else if (warp >= 4) {
+    if (timing && lane == 0) {
+      cp.dbg[b * CT_SLOTS + CT_CHK_ITERS] = c_iters;
+      cp.dbg[b * CT_SLOTS + CT_CHK_FENCE] = c_fence;
+      cp.dbg[b * CT_SLOTS + CT_CHK_HITS] = c_hits;
+      cp.dbg[b * CT_SLOTS + CT_CHK_TOTAL] = clock64() - c_t0;
+    }
+  } else if (warp >= 4 && warp < 12) {
     // ============================================================ epilogue (2 groups alternate tiles)
     const int grp = (warp - 4) >> 2;
     const int gtid = threadIdx.x - 128 - grp * 128;
@@ -547,7 +558,11 @@ conv_chain_kernel(const __grid_constant__ ChainParams cp) {
         }
       }
       if (gtid == 0) CT_TRACE(g, 2);
-      if (l + 1 < L && !(xf & 4u)) {
+      if (l + 1 < L && (xf & 128u)) {
+        // ablation: publish right behind the stores (group barrier + fence + flag), no deferral
+        named_bar_sync(1 + grp, 128);
+        if (gtid == 0) { fence_acq_rel_gpu(); st_relaxed_gpu(flags + tile, fbase + (uint32_t)l + 1u); CT_TRACE(g, 3); }
+      } else if (l + 1 < L && !(xf & 4u)) {
         pending = true;
         pend_flag = flags + tile;
         pend_val = fbase + (uint32_t)l + 1u;

@@ -2,11 +2,12 @@
 (tecogan-pytorch_b200/csrc/tg_chain_tcgen05.cu) -- CPU only, no GPU, no library call.
 
 The kernel chains 64->64 convolutions inside one persistent launch; its correctness rests on a
-protocol between five roles per CTA (TMA producer, MMA issuer, weight streamer, dependency checker,
-two epilogue groups) and on per-tile progress flags between CTAs.  Every role below is a transcription
+protocol between six roles per CTA (TMA producer, two MMA issuers, weight streamer, dependency
+checker, two epilogue groups) and on per-tile progress flags between CTAs.  Every role below is a transcription
 of the corresponding loop of the kernel as a Python generator; asynchronous hardware (TMA
-completions, the in-order tensor pipe with its tcgen05.commit arrivals) is modelled by event queues
-that a seeded random scheduler drains in arbitrary interleavings.  The model checks, for many
+completions, the tensor pipe with its tcgen05.commit arrivals -- in order per issuing thread, NO order
+assumed between the two issuers) is modelled by event queues that a seeded random scheduler drains in
+arbitrary interleavings.  The model checks, for many
 shapes (tiles per CTA from 1 up, 1..6 layers, in-place residual buffers like SRNet's) and schedules:
 
   * no deadlock: some role or event can always make progress until every tile of every layer is done;
@@ -14,19 +15,22 @@ shapes (tiles per CTA from 1 up, 1..6 layers, in-place residual buffers like SRN
     (the kernel waits on parities, so a second completion would make the wait hang);
   * RAW on activations: when a tile's TMA box lands, every tile under its halo holds the previous
     layer's output -- not older (not yet produced) and not newer (overwritten in place too early);
-  * the weight ring: when an MMA executes, the slot it reads holds this layer's tap.
+  * the weight double buffer: when an MMA executes, buffer l & 1 holds this layer's weights.
 
-It reproduces the two bugs that bring-up hit on the GPU (`lookahead_blocks=True`: the MMA issuer
-blocking on the next tile's data before committing the current one; `gate_streamer=False`: the
-streamer completing a weight barrier twice before the issuer's first wait), and it found a third one
-that the GPU tests never triggered (`gate_early=False`: with one tile per CTA a delayed streamer
-could find a hand-over barrier two phases ahead) -- see test_model_catches_the_protocol_bugs.
+It reproduces the bugs that bring-up hit on the GPU (`lookahead_blocks=True`: an MMA issuer blocking on its
+next tile's data before committing the current one; `full_per_issuer=False`: two issuers sharing three A
+stages, whose parity waits then pass two fills early) and the ones it found while the second issuer was
+designed (`refill_waits_both=False`: a weight buffer overwritten under the slower issuer's MMAs;
+`visit_empty_layers=False`: with one tile per CTA and layer the refill barrier never completes) -- see
+test_model_catches_the_protocol_bugs.  Round 1's 14-slot weight ring (wstart / wearly gates) was replaced by
+the double buffer when the second issuer came in: a 15-slot ring + four A stages was modelled and measured
+too, and lost to the stall at every layer boundary.
 """
 import random
 
 import pytest
 
-STAGES, BUFS, SLOTS, WINDOW = 4, 8, 14, 9
+STAGES, BUFS, WINDOW = 3, 8, 3
 
 
 class ProtocolError(AssertionError):
@@ -49,6 +53,10 @@ class MBar:
     def done(self, k, who=''):
         if self.phase >= k + 2:
             raise ProtocolError(f'{who}: barrier is {self.phase - k} phases past the awaited completion {k}')
+        if self.phase < k:
+            # completion k - 2 has the parity of completion k: the kernel's parity wait would PASS here
+            raise ProtocolError(f'{who}: waiting for completion {k} of a barrier that has only completed {self.phase} '
+                                f'(a waiter must observe every completion of a barrier it waits on by parity)')
         return self.phase == k + 1
 
 
@@ -58,18 +66,23 @@ class Cta:
         s = sim
         self.n_my = (s.num_tiles - 1 - b) // s.G + 1
         self.total = s.L * self.n_my
-        self.full = [MBar() for _ in range(STAGES)]
-        self.empty = [MBar() for _ in range(STAGES)]
+        # one set of 'A tile landed' barriers PER ISSUER: with an odd stage count an issuer meets a stage only
+        # every other time it is filled, and a parity wait needs to see every completion
+        self.full = [[MBar() for _ in range(self.sim.stages)] for _ in range(2 if sim.full_per_issuer else 1)]
+        self.full_use, cnt = {}, {}
+        for seq in range(self.total):
+            key = ((seq & 1) if sim.full_per_issuer else 0, seq % self.sim.stages)
+            self.full_use[seq] = cnt.get(key, 0)
+            cnt[key] = self.full_use[seq] + 1
+        self.empty = [MBar() for _ in range(self.sim.stages)]
         self.tfull = [MBar() for _ in range(BUFS)]
         self.tempty = [MBar(1) for _ in range(BUFS)]      # one arrival per epilogue group (4 warps in the kernel)
-        self.wfull = [MBar() for _ in range(9)]
-        self.wfree = [MBar() for _ in range(9)]
-        self.wstart = MBar()
-        self.wearly = MBar()
+        self.wfull = [MBar() for _ in range(2)]          # weights of layer l landed in buffer l & 1
+        self.wfree = [MBar(2 if sim.refill_waits_both else 1) for _ in range(2)]   # both issuers retired the layer
         self.deps_ok = self.n_my                         # layer 0 has no dependencies
-        self.stage_tile = [None] * STAGES                # what the A stage holds (seq) once landed
-        self.slot = [None] * SLOTS                       # (layer, tap) each weight slot holds
-        self.pipe = []                                   # in-order tensor pipe: ('mma', seq, tap) | ('commit', MBar)
+        self.stage_tile = [None] * self.sim.stages                # what the A stage holds (seq) once landed
+        self.wbuf = [None, None]                         # layer each weight buffer holds
+        self.pipes = [[], []]                            # per issuer, in order: ('mma', seq) | ('commit', MBar)
         self.loads = []                                  # in-flight TMA / bulk loads: callables
         self.done_tiles = 0
 
@@ -85,7 +98,7 @@ class Cta:
             if l > 0:
                 while self.deps_ok <= seq:
                     yield
-            st, use = seq % STAGES, seq // STAGES
+            st, use = seq % self.sim.stages, seq // self.sim.stages
             if use > 0:
                 while not self.empty[st].done(use - 1, 'producer/empty'):
                     yield
@@ -96,75 +109,73 @@ class Cta:
     def _land(self, st, seq, l, t):
         self.sim.check_halo_ready(l, t, 'TMA landing')    # nobody overwrote the halo in the meantime
         self.stage_tile[st] = seq
-        self.full[st].arrive()
+        self.fullbar(seq).arrive()
 
-    def mma(self):
+    def fullbar(self, seq):
+        return self.full[(seq & 1) if self.sim.full_per_issuer else 0][seq % self.sim.stages]
+
+    def mma(self, w):
+        """issuer w owns seq = w, w + 2, ...; it ENTERS every layer in order (waits for its weights) and EXITS it
+        (an arrival on wfree[l & 1]: a commit behind its last tile of the layer, or a plain arrive when it has
+        no tile there)"""
         s = self.sim
-        while not (self.full[0].done(0, 'mma/full')):
-            yield
-        for seq in range(self.total):
+        pipe = self.pipes[w]
+        entered = -1
+        if w < self.total:
+            while not self.fullbar(w).done(0, 'mma/full'):
+                yield
+        for seq in range(w, self.total, 2):
             l, k, t = self.tile(seq)
-            first_k, last_k = k == 0, k == self.n_my - 1
-            hand_over = last_k and l + 1 < s.L
-            st, buf = seq % STAGES, seq % BUFS
-            nst, nbuf = (seq + 1) % STAGES, (seq + 1) % BUFS
-            if first_k:
-                for tap in range(9):
-                    while not self.wfull[tap].done(l, 'mma/wfull'):
-                        yield
-                self.wstart.arrive()
-            if hand_over and s.gate_early:
-                # the streamer must have consumed the PREVIOUS completion of wfree[4..8] (its waits for
-                # the next layer's taps 0-4) before this layer's hand-over completes them again
-                while not self.wearly.done(l, 'mma/wearly'):
+            nl = (seq + 2) // self.n_my
+            last_mine = nl != l
+            has_next = seq + 2 < self.total
+            st, buf = seq % self.sim.stages, seq % BUFS
+            nst, nbuf = (seq + 2) % self.sim.stages, (seq + 2) % BUFS
+            while entered < l:
+                entered += 1
+                if entered < l and not s.visit_empty_layers:
+                    continue
+                while not self.wfull[entered & 1].done(entered >> 1, 'mma/wfull'):
                     yield
+                if entered < l:
+                    self.wfree[entered & 1].arrive()
             next_ready = False
+
+            def ready():
+                a = (seq + 2) < BUFS or self.tempty[nbuf].done((seq + 2) // BUFS - 1, 'mma/tempty')
+                return a and self.fullbar(seq + 2).done(self.full_use[seq + 2], 'mma/full')
             for part in range(2):
-                for tap in (range(0, 4) if part == 0 else range(4, 9)):
-                    self.pipe.append(('mma', seq, tap))
-                if hand_over:
-                    for tap in (range(0, 4) if part == 0 else range(4, 9)):
-                        self.pipe.append(('commit', self.wfree[tap]))
+                pipe.append(('mma', seq))
                 if part == 1:
-                    self.pipe.append(('commit', self.empty[st]))
-                    self.pipe.append(('commit', self.tfull[buf]))
-                if part == 0 and seq + 1 < self.total:
-                    def ready():
-                        a = (seq + 1) < BUFS or self.tempty[nbuf].done((seq + 1) // BUFS - 1, 'mma/tempty')
-                        return a and self.full[nst].done((seq + 1) // STAGES, 'mma/full')
+                    pipe.append(('commit', self.empty[st]))
+                    pipe.append(('commit', self.tfull[buf]))
+                    if last_mine:
+                        pipe.append(('commit', self.wfree[l & 1]))
+                if part == 0 and has_next:
                     if s.lookahead_blocks:                # the bring-up bug: a blocking wait here
                         while not ready():
                             yield
                     next_ready = ready()
                 yield
-            if seq + 1 < self.total and not next_ready:
-                while not ((seq + 1) < BUFS or self.tempty[nbuf].done((seq + 1) // BUFS - 1, 'mma/tempty')):
+            if has_next and not next_ready:
+                while not ((seq + 2) < BUFS or self.tempty[nbuf].done((seq + 2) // BUFS - 1, 'mma/tempty')):
                     yield
-                while not self.full[nst].done((seq + 1) // STAGES, 'mma/full'):
+                while not self.fullbar(seq + 2).done(self.full_use[seq + 2], 'mma/full'):
                     yield
 
     def streamer(self):
         s = self.sim
-        for tap in range(9):                              # layer 0, before anything else
-            self.loads.append(lambda tap=tap: self._wland(0, tap))
-        for l in range(1, s.L):
-            if s.gate_streamer:
-                while not self.wstart.done(l - 1, 'streamer/wstart'):
-                    yield
-            for tap in range(9):
-                gi = 9 * l + tap
-                if gi >= SLOTS:
-                    pl, pt = divmod(gi - SLOTS, 9)
-                    while not self.wfree[pt].done(pl, 'streamer/wfree'):
-                        yield
-                self.loads.append(lambda l=l, tap=tap: self._wland(l, tap))
-                if tap == SLOTS - 9 - 1:
-                    self.wearly.arrive()                  # the waits that refer to layer l-2 are behind us
+        for l in range(min(2, s.L)):                      # the first two layers, before anything else
+            self.loads.append(lambda l=l: self._wland(l))
+        for l in range(2, s.L):
+            while not self.wfree[l & 1].done((l - 2) >> 1, 'streamer/wfree'):
                 yield
+            self.loads.append(lambda l=l: self._wland(l))
+            yield
 
-    def _wland(self, l, tap):
-        self.slot[(9 * l + tap) % SLOTS] = (l, tap)
-        self.wfull[tap].arrive()
+    def _wland(self, l):
+        self.wbuf[l & 1] = l
+        self.wfull[l & 1].arrive()
 
     def checker(self):
         s = self.sim
@@ -207,27 +218,29 @@ class Cta:
             s.publish(*pending)
 
     # ------------------------------------------------------------------ asynchronous hardware
-    def retire_one(self):
-        """the tensor pipe retires its oldest entry"""
-        kind, *rest = self.pipe.pop(0)
+    def retire_one(self, w):
+        """the tensor pipe retires the oldest entry of issuer w"""
+        kind, *rest = self.pipes[w].pop(0)
         if kind == 'commit':
             rest[0].arrive()
             return
-        seq, tap = rest
+        seq = rest[0]
         l, k, t = self.tile(seq)
-        if self.stage_tile[seq % STAGES] != seq:
-            raise ProtocolError(f'cta {self.b}: MMA of seq {seq} reads stage holding {self.stage_tile[seq % STAGES]}')
-        if self.slot[(9 * l + tap) % SLOTS] != (l, tap):
-            raise ProtocolError(f'cta {self.b}: MMA layer {l} tap {tap} reads slot holding '
-                                f'{self.slot[(9 * l + tap) % SLOTS]}')
+        if self.stage_tile[seq % self.sim.stages] != seq:
+            raise ProtocolError(f'cta {self.b}: MMA of seq {seq} reads stage holding {self.stage_tile[seq % self.sim.stages]}')
+        if self.wbuf[l & 1] != l:
+            raise ProtocolError(f'cta {self.b}: MMA of layer {l} reads a weight buffer holding layer {self.wbuf[l & 1]}')
 
 
 class Sim:
-    def __init__(self, tiles_x, tiles_y, n, G, L, seed, lookahead_blocks=False, gate_streamer=True, gate_early=True):
+    def __init__(self, tiles_x, tiles_y, n, G, L, seed, lookahead_blocks=False, refill_waits_both=True,
+                 visit_empty_layers=True, full_per_issuer=True, stages=STAGES):
         self.tiles_x, self.tiles_y, self.n, self.L = tiles_x, tiles_y, n, L
         self.num_tiles = tiles_x * tiles_y * n
         self.G = min(G, self.num_tiles)
-        self.lookahead_blocks, self.gate_streamer, self.gate_early = lookahead_blocks, gate_streamer, gate_early
+        self.lookahead_blocks, self.refill_waits_both, self.visit_empty_layers, self.full_per_issuer = (
+            lookahead_blocks, refill_waits_both, visit_empty_layers, full_per_issuer)
+        self.stages = stages
         self.rng = random.Random(seed)
         self.flag = [0] * self.num_tiles                  # layers published per tile
         # SRNet buffer plan: layer 0: x(0) -> 1; odd layers: 1 -> 2; even layers > 0: 2 -> 1 (in place over
@@ -263,21 +276,22 @@ class Sim:
     def run(self, max_steps=2_000_000):
         actors = []
         for c in self.ctas:
-            actors += [c.producer(), c.mma(), c.streamer(), c.checker(), c.epilogue(0), c.epilogue(1)]
+            actors += [c.producer(), c.mma(0), c.mma(1), c.streamer(), c.checker(), c.epilogue(0), c.epilogue(1)]
         live = list(actors)
         idle = 0
         for _ in range(max_steps):
-            if not live and not any(c.pipe or c.loads for c in self.ctas):
+            if not live and not any(c.pipes[0] or c.pipes[1] or c.loads for c in self.ctas):
                 break
             before = self._snapshot()
             r = self.rng.random()
-            hw = [c for c in self.ctas if c.pipe or c.loads]
+            hw = [c for c in self.ctas if c.pipes[0] or c.pipes[1] or c.loads]
             if hw and (r < 0.35 or not live):
                 c = self.rng.choice(hw)
-                if c.loads and (not c.pipe or self.rng.random() < 0.5):
+                busy = [w for w in (0, 1) if c.pipes[w]]
+                if c.loads and (not busy or self.rng.random() < 0.5):
                     c.loads.pop(self.rng.randrange(len(c.loads)))()      # loads complete in any order
                 else:
-                    c.retire_one()
+                    c.retire_one(self.rng.choice(busy))
             else:
                 a = self.rng.choice(live)
                 try:
@@ -293,9 +307,9 @@ class Sim:
         assert all(v == self.L - 1 for v in self.version[self.dst[self.L - 1]])
 
     def _snapshot(self):
-        return (tuple(self.flag), tuple(c.done_tiles for c in self.ctas), tuple(len(c.pipe) for c in self.ctas),
+        return (tuple(self.flag), tuple(c.done_tiles for c in self.ctas), tuple(len(c.pipes[0]) + len(c.pipes[1]) for c in self.ctas),
                 tuple(len(c.loads) for c in self.ctas), tuple(c.deps_ok for c in self.ctas),
-                tuple(b.phase for c in self.ctas for b in c.full + c.tfull + c.wfull + c.wfree + [c.wstart, c.wearly]))
+                tuple((b.phase, b.arrived) for c in self.ctas for b in sum(c.full, []) + c.tfull + c.wfull + c.wfree))
 
 
 SHAPES = [
@@ -319,17 +333,24 @@ def test_chain_protocol_random_schedules(shape):
 
 def test_model_catches_the_protocol_bugs():
     # (1) a BLOCKING look-ahead on the next tile's barriers before the current tile is committed
-    #     deadlocks as soon as the next tile depends on the current one (one tile per CTA)
+    #     deadlocks as soon as the next tile depends on the current one (few tiles per CTA)
     with pytest.raises(ProtocolError, match='deadlock'):
+        for seed in range(8):
+            Sim(3, 2, 1, 3, 3, seed=seed, lookahead_blocks=True).run()
+    # (2) a weight buffer refilled after ONE issuer's exit is overwritten under the other issuer's MMAs
+    with pytest.raises(ProtocolError, match='weight buffer|phases past|observe every'):
+        for seed in range(40):
+            Sim(3, 2, 1, 2, 5, seed=seed, refill_waits_both=False).run()
+    # (3) with one tile per CTA and layer each issuer has tiles in every other layer only: unless it also
+    #     enters and exits the layers in between, the refill barrier (count 2) never completes
+    with pytest.raises(ProtocolError, match='deadlock|observe every'):
         for seed in range(4):
-            Sim(3, 2, 1, 8, 3, seed=seed, lookahead_blocks=True).run()
-    # (2) without the wstart gate the streamer can complete a weight barrier's second phase before the
-    #     MMA issuer has waited for the first one: a parity wait would then hang
-    with pytest.raises(ProtocolError, match='phases past'):
-        for seed in range(40):
-            Sim(3, 2, 1, 4, 4, seed=seed, gate_streamer=False).run()
-    # (3) without the wearly gate a streamer that is scheduled late (one tile per layer) finds the
-    #     hand-over barrier of taps 4-8 completed twice
-    with pytest.raises(ProtocolError, match='streamer/wfree'):
-        for seed in range(40):
-            Sim(1, 1, 1, 1, 4, seed=seed, gate_early=False).run()
+            Sim(3, 2, 1, 8, 5, seed=seed, visit_empty_layers=False).run()
+    # (4) three A stages shared by two issuers: an issuer meets a stage only every other time it is filled, so
+    #     a parity wait on a shared 'landed' barrier passes two fills early (hit on the GPU: garbage and hangs);
+    #     the kernel keeps one set of 'landed' barriers per issuer (an even stage count would do as well)
+    with pytest.raises(ProtocolError, match='observe every completion'):
+        for seed in range(8):
+            Sim(3, 2, 1, 1, 3, seed=seed, full_per_issuer=False).run()
+    for seed in range(4):
+        Sim(3, 2, 1, 1, 3, seed=seed, stages=4, full_per_issuer=False).run()

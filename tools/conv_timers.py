@@ -55,7 +55,8 @@ def run(name, cin, cout_real, h, w, n, kind=L.CONV_3X3, epilogue=L.EPI_NHWC_F16,
 
 
 CHAIN_NAMES = ['prod_wait_flags', 'prod_wait_empty', 'mma_total', 'mma_wait', 'epi_wait_tfull', 'epi_total',
-               'kernel', 'tiles', 'mma_issue0', 'mma_look', 'mma_issue1', 'mma_boundary']
+               'kernel', 'tiles', 'mma_issue0', 'mma_look', 'mma_issue1', 'mma_boundary',
+               'chk_iters', 'chk_fence', 'chk_hits', 'chk_total']
 
 
 def run_chain(blocks=10, n=4, h=134, w=320):
@@ -117,7 +118,7 @@ def run_chain(blocks=10, n=4, h=134, w=320):
         'lead: TMA issue(q) - MMA start(q-3)': tr[sel, 5] - tr[sel - 3, 6],
     }
     print(json.dumps({'trace_cta0 p10/p50/p90 cycles': {k: stat(v) for k, v in ev.items()}}))
-    q = torch.quantile(full[:, :12], torch.tensor([0.0, 0.5, 1.0], dtype=torch.double), dim=0)
+    q = torch.quantile(full[:, :16], torch.tensor([0.0, 0.5, 1.0], dtype=torch.double), dim=0)
     print(json.dumps({'min/med/max': {nm: [int(q[j, i].item()) for j in range(3)] for i, nm in enumerate(CHAIN_NAMES)}}))
     return out
 
@@ -140,7 +141,7 @@ def run_chain_ablate(n=4, h=134, w=320, blocks=10, max_ctas=0):
         chain(bufs)
     lib = L.load()
     buf = torch.zeros(148 * 16 + 8 * 24 * 16, dtype=torch.int64, device=dev)
-    combos = [0, 1, 5, 2, 3, 7, 7 + 32, 8 + 7, 16, 16 + 7, 16 + 15, 16 + 15 + 32, 8, 32]
+    combos = [int(c) for c in os.environ.get('TG_ABLATE_COMBOS', '0,1,5,2,3,7,39,15,16,23,31,63,8,32,64,128,192,194').split(',')]
     for fl in combos:
         os.environ['TG_CHAIN_ABLATE'] = str(fl)
         buf.zero_()

@@ -156,6 +156,72 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(unsigned int* out) {
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// Two issuing warps (one elected lane each, own accumulator and barrier), G cycles of unrelated work
+// after EVERY MMA: does a second issuer hide the first one's bookkeeping?
+template <int G, int WARPS>
+__global__ void __launch_bounds__(128, 1) probe2_kernel(unsigned int* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bar = base;
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(sm + 32);
+  const uint32_t a0 = base + 1024, b0 = base + 1024 + 64 * 1024;
+  for (int i = threadIdx.x; i < (200 * 1024 - 2048) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sm + 1024)[i] = 0x2C002C00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 8, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_s)), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_s;
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0);
+  if (warp < WARPS && elect_one_sync()) {
+    const uint64_t a_hi = make_sdesc(0, 10u * 128u), b_hi = make_sdesc(0, 1024u);
+    const uint32_t sa16 = ((a0 + warp * 32768u) & 0x3FFFFu) >> 4, sb16 = (b0 & 0x3FFFFu) >> 4;
+    const uint32_t idesc = idesc_for(64);
+    const uint32_t d = tmem + warp * 256u;
+    const unsigned int t0 = vclock();
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      const int j = i % 36, tap = j >> 2, kk = j & 3;
+      const uint32_t aoff = (uint32_t)((tap / 3) * 10 + tap % 3) * 8u + 2u * kk;
+      umma_f16(d, a_hi | (uint64_t)(sa16 + aoff), b_hi | (uint64_t)(sb16 + (uint32_t)tap * 512u + 2u * kk), idesc, i >= 1);
+      if (G) {
+        const unsigned int g0 = vclock();
+        while (vclock() - g0 < (unsigned)G) { }
+      }
+    }
+    umma_commit(bar + 8 * warp);
+    mbar_wait(bar + 8 * warp, 0, 3);
+    const unsigned int t2 = vclock();
+    out[blockIdx.x * 2 + warp] = t2 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
+template <int G, int WARPS>
+void run_probe2(int grid, int smem) {
+  unsigned int* d = nullptr;
+  cudaMalloc(&d, grid * 8);
+  cudaMemset(d, 0, grid * 8);
+  cudaFuncSetAttribute(probe2_kernel<G, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int rep = 0; rep < 2; ++rep) probe2_kernel<G, WARPS><<<grid, 128, smem>>>(d);
+  cudaDeviceSynchronize();
+  std::vector<unsigned int> h(grid * 2);
+  cudaMemcpy(h.data(), d, grid * 8, cudaMemcpyDeviceToHost);
+  std::vector<double> t;
+  for (int b = 0; b < grid; ++b) t.push_back(std::max(h[2 * b], h[2 * b + 1]));
+  std::sort(t.begin(), t.end());
+  printf("issuers=%d, %3d cycles of other work after every MMA: %6.0f cycles for %d MMAs per issuer = %.1f cycles per MMA (all issuers)\n",
+         WARPS, G, t[t.size() / 2], K, t[t.size() / 2] / (K * WARPS));
+  cudaFree(d);
+}
+
 }  // namespace
 
 template <int... Vs>
@@ -197,5 +263,9 @@ int main(int argc, char** argv) {
     }
   }
   cudaFree(d_out);
+  run_probe2<0, 1>(grid, smem);  run_probe2<0, 2>(grid, smem);
+  run_probe2<20, 1>(grid, smem); run_probe2<20, 2>(grid, smem);
+  run_probe2<40, 1>(grid, smem); run_probe2<40, 2>(grid, smem);
+  run_probe2<80, 1>(grid, smem); run_probe2<80, 2>(grid, smem);
   return 0;
 }

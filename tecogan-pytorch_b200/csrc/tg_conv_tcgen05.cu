@@ -81,6 +81,14 @@ enum { T_PROD_WAIT_EMPTY = 0, T_MMA_WAIT_TEMPTY, T_MMA_WAIT_FULL, T_MMA_ISSUE, T
 #define TG_T0() (timing ? clock64() : 0)
 #define TG_ACC(var, t0) do { if (timing) var += clock64() - (t0); } while (0)
 
+// two MMA issuer warps (1 and 3) instead of one: halo convs whose tile is one smem stage, with even stage and
+// accumulator counts (TG_DBG_FLAGS bit 16 = single issuer, for A/B measurements)
+template <int MODE>
+__device__ __forceinline__ bool conv_dual_issue(const KParams& p) {
+  return MODE == MODE_HALO && p.chunks == 1 && p.n_stages >= 2 && (p.n_stages & 1) == 0 && p.n_buf >= 2 &&
+         !(p.dbg_flags & 16);
+}
+
 struct TileCoord { int n, y0, x0, nb; };
 __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
   TileCoord t;
@@ -108,7 +116,9 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
   const uint32_t base = (raw + 1023u) & ~1023u;   // 128B swizzle atoms need 1024B alignment
   uint8_t* sm = smem_raw + (base - raw);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffle broadcast: the compiler then knows the warp index is warp-uniform and keeps role-loop counters,
+  // barrier addresses and UMMA descriptors in uniform registers (no R2UR in front of every MMA)
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const tg_conv_desc& d = p.d;
   constexpr bool timing = TIMING;   // role timers compiled out of the production instantiation
   const long long t_kernel0 = timing ? clock64() : 0;
@@ -216,14 +226,72 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
       }
       if (timing) p.dbg[blockIdx.x * T_SLOTS + T_PROD_WAIT_EMPTY] = tw;
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer
+  } else if (warp == 1 || (warp == 3 && conv_dual_issue<MODE>(p))) {
+    // ============================================================ MMA issuer(s)
     // One warp consumes the smem stages strictly in order (a parity wait is only sound while the
     // waiter is at most one phase ahead of the barrier).  The fixed latencies between tiles
     // (mbarrier polls, commit -> epilogue hand-off, MMA pipeline fill/drain) are hidden by depth
     // instead: up to n_buf accumulator buffers are in flight in TMEM.  The warp walks the
     // (warp-uniform) pipeline; one elected lane issues.
-    {
+    if (conv_dual_issue<MODE>(p)) {
+      // TWO issuers (warps 1 and 3) take the tiles of this CTA alternately: an N=64 MMA holds the tensor pipe
+      // for 48 cycles and the pipe hides only ~180 cycles without a new instruction, while one warp needs
+      // ~80 cycles per MMA for issue + bookkeeping (tools/mma_probe.cu) -- with one issuer the pipe idles
+      // 40 % of the time.  Stage it % n_stages, accumulator it % n_buf, both counts even: a stage / buffer
+      // always belongs to the same issuer, who therefore sees every completion of the barriers it waits on
+      // by parity.  All lanes walk the loop on warp-uniform values (uniform datapath), one elected lane issues.
+      const int w = warp == 1 ? 0 : 1;
+      if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
+      constexpr int kBoxW = (KIND == TG_CONV_3X3) ? TW + 2 : TW + 1;
+      constexpr int kOrg = (KIND == TG_CONV_3X3) ? -1 : 0;
+      const uint32_t a_hi32 = (uint32_t)(make_sdesc(0, (uint32_t)kBoxW * 128u) >> 32);
+      const uint32_t b_hi32 = (uint32_t)(make_sdesc(0, 1024u) >> 32);
+      const uint32_t a_lo0 = ((smem_stage0 & 0x3FFFFu) >> 4) + 0x10000u;   // + LBO field (1 << 16)
+      const uint32_t b_lo0 = ((smem_b & 0x3FFFFu) >> 4) + 0x10000u;
+      const uint32_t btb16 = p.b_stage_bytes >> 4;
+      const uint32_t st16 = p.stage_bytes >> 4;
+      int stage = w, buf = w, it = 0;
+      uint32_t phase = 0, bphase = 0;
+      long long tw_tempty = 0, tw_full = 0, t_issue = 0;
+      const bool tm = timing && w == 0;
+      const long long t_mma0 = tm ? clock64() : 0;
+      for (int tile = blockIdx.x + w * (int)gridDim.x; tile < p.num_tiles; tile += 2 * (int)gridDim.x, ++it) {
+        long long t0 = tm ? clock64() : 0;
+        mbar_wait(bar_tempty + 8 * buf, bphase ^ 1, 4);
+        if (tm) { tw_tempty += clock64() - t0; t0 = clock64(); }
+        mbar_wait(bar_full + 8 * stage, phase, 5);
+        if (tm) { tw_full += clock64() - t0; t0 = clock64(); }
+        tc_fence_after();
+        const uint32_t sa = a_lo0 + (uint32_t)stage * st16;
+        const uint32_t d_base = tmem_base + (uint32_t)buf * p.acc_stride;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int g = 0; g < 9; ++g) {
+            const TgGroup gr = tg_group(KIND, g);
+            const bool first_of_acc = (g == 0) || (tg_group(KIND, g > 0 ? g - 1 : 0).acc != gr.acc);
+            const uint32_t off = (uint32_t)((gr.dy - kOrg) * kBoxW + (gr.dx - kOrg)) * 8u;
+            const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_words(dcol, sa + off + 2u * k, a_hi32, b_lo0 + (uint32_t)g * btb16 + 2u * k, b_hi32, p.idesc,
+                             (first_of_acc && k == 0) ? 0u : 1u);
+          }
+          umma_commit(bar_empty + 8 * stage);
+          umma_commit(bar_tfull + 8 * buf);
+        }
+        __syncwarp();
+        if (tm) t_issue += clock64() - t0;
+        stage += 2;
+        if (stage >= p.n_stages) { stage -= p.n_stages; phase ^= 1u; }
+        buf += 2;
+        if (buf >= p.n_buf) { buf -= p.n_buf; bphase ^= 1u; }
+      }
+      if (tm && lane == 0) {
+        unsigned long long* o = p.dbg + blockIdx.x * T_SLOTS;
+        o[T_MMA_WAIT_TEMPTY] = tw_tempty; o[T_MMA_WAIT_FULL] = tw_full; o[T_MMA_ISSUE] = t_issue;
+        o[T_MMA_TOTAL] = clock64() - t_mma0; o[T_TILES] = 2 * it;
+      }
+    } else {
       if (p.b_resident) { mbar_wait(bar_b, 0, 3); }
       int stage = 0;
       uint32_t phase = 0;
@@ -805,8 +873,9 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   }
   const uint32_t avail = kSmemLimit - fixed - (p.b_resident ? b_total : 0u);
   int stages = (int)(avail / p.stage_bytes);
-  const int want = p.halo ? 5 : kMaxStages;
+  const int want = p.halo ? 6 : kMaxStages;
   if (stages > want) stages = want;
+  if (p.halo && p.chunks == 1 && stages >= 2) stages &= ~1;   // even: each of the two MMA issuers owns its stages
   TG_REQUIRE(stages >= 2, TG_E_UNSUPPORTED, "conv_tcgen05: shared memory budget (cin=%d cout=%d)", d->cin, d->cout);
   p.n_stages = stages;
   p.off_b = kHeaderBytes;

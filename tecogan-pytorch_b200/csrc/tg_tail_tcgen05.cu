@@ -122,6 +122,8 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
+  // (a shuffle-broadcast warp index, which helps the other tcgen05 kernels, makes this one 45 % slower: measured
+  // 264 vs 182 us -- the epilogue roles lose registers to the uniform-path bookkeeping)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const uint32_t bar_full = base;              // [2] halo stage landed

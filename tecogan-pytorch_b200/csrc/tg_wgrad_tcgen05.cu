@@ -90,7 +90,9 @@ wgrad_tcgen05_kernel(const __grid_constant__ WParams p) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffle broadcast: the compiler then knows the warp index is warp-uniform and keeps role-loop counters,
+  // barrier addresses and UMMA descriptors in uniform registers (no R2UR in front of every MMA)
+  const int warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   const uint32_t bar_full = base;                       // [kMaxStages]
   const uint32_t bar_empty = base + 8 * kMaxStages;     // [kMaxStages]

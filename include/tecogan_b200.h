@@ -126,7 +126,9 @@ typedef struct tg_conv_desc {
   int32_t epilogue;     /* TG_EPI_*                                                      */
   int32_t a_mode;       /* TG_AMODE_* (tcgen05 kernel only; AUTO = fastest validated)    */
   int32_t max_ctas;     /* 0 = one persistent CTA per SM                                 */
-  int32_t reserved;     /* must be 0                                                     */
+  int32_t cin_real;     /* input channels that can be non-zero (0 = cin): for cin = 64 the tcgen05 kernel skips the
+                           UMMA k-steps of 16 channels at or beyond it -- the packed weights are zero there, so the
+                           result is bit-identical (thin layers: FNet 6->32, 32->32, 32->64, 32->2)  */
   const void* mask;     /* TG_ACT_DRELU / TG_ACT_DLRELU02: NHWC fp16, shape of y; else NULL */
 } tg_conv_desc;
 

@@ -67,6 +67,7 @@ struct KParams {
   int n_buf;                       // accumulator buffers in flight (512 / acc_stride, <= 8, even)
   int dbg_flags;                   // diagnostics (TG_DBG_FLAGS): 1 = TAPN skip global RMW, 2 = skip exchange
   int n_stages;
+  int ksteps;                      // UMMA k-steps (16 channels) per 64-channel chunk that can hold non-zero input (1..4)
   int n_split, bn;                 // output channels are split over n_split CTAs of bn columns
   uint32_t stage_bytes, a_bytes, b_tile_bytes, b_stage_bytes;
   uint32_t off_b, off_stage, off_staging;
@@ -273,7 +274,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
             const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_words(dcol, sa + off + 2u * k, a_hi32, b_lo0 + (uint32_t)g * btb16 + 2u * k, b_hi32, p.idesc,
+              if (k < p.ksteps) umma_f16_words(dcol, sa + off + 2u * k, a_hi32, b_lo0 + (uint32_t)g * btb16 + 2u * k, b_hi32, p.idesc,
                              (first_of_acc && k == 0) ? 0u : 1u);
           }
           umma_commit(bar_empty + 8 * stage);
@@ -352,6 +353,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
               const uint32_t dcol = (uint32_t)gr.acc * (uint32_t)p.bn;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
+                if (k >= p.ksteps) continue;
                 const uint32_t accf = (first_of_acc && k == 0) ? 0u : 1u;
                 umma_f16(dA + dcol, a_hi | (uint64_t)(saA + off + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc, accf);
                 if (two)
@@ -399,7 +401,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
                 const uint32_t dcol = tmem_base + bufs[j] * acc_stride;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(dcol, a_hi | (uint64_t)(sa16 + 2u * k), b_hi | (uint64_t)(smem_b16 + 2u * k), p.idesc,
+                  if (k < p.ksteps) umma_f16(dcol, a_hi | (uint64_t)(sa16 + 2u * k), b_hi | (uint64_t)(smem_b16 + 2u * k), p.idesc,
                            k == 0 ? 0u : 1u);
                 umma_commit(bar_empty + 8 * sts[j]);
                 umma_commit(bar_tfull + 8 * bufs[j]);
@@ -444,7 +446,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
                   const uint32_t dcol = d_base + (uint32_t)gr.acc * (uint32_t)p.bn;
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
-                    umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
+                    if (k < p.ksteps) umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
                              (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
                 }
                 if (part == 1) {
@@ -483,7 +485,7 @@ conv_tcgen05_kernel(const __grid_constant__ TgMaps maps, const KParams p) {
               if (elect_one_sync()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
+                  if (k < p.ksteps) umma_f16(dcol, a_hi | (uint64_t)(a16 + 2u * k), b_hi | (uint64_t)(b16 + 2u * k), p.idesc,
                            (first_of_acc && k == 0 && c == 0) ? 0u : 1u);
                 umma_commit(bar_empty + 8 * stage);
                 if (last) umma_commit(bar_tfull + 8 * buf);
@@ -811,6 +813,9 @@ int tg_conv_tcgen05(const tg_conv_desc* d, void* stream) {
   p.tiles_y = tg_ceil_div(d->h, p.step_y);
   p.num_tiles = p.tiles_x * p.tiles_y * d->n;
   p.chunks = d->cin / 64;
+  TG_REQUIRE(d->cin_real >= 0 && d->cin_real <= d->cin, TG_E_INVALID, "conv_tcgen05: cin_real=%d outside [0, cin=%d]",
+             d->cin_real, d->cin);
+  p.ksteps = (p.chunks == 1 && d->cin_real > 0) ? (d->cin_real + 15) / 16 : 4;
   p.n_acc = d->kind == TG_CONVT_3X3_S2 ? 4 : 1;
   p.b_tile_bytes = (uint32_t)d->cout * 128u;
 

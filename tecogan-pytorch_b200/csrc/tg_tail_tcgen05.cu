@@ -83,7 +83,7 @@ struct TailParams {
 };
 // role-timer slots (cycles per CTA): tools/conv_timers.py tail
 enum { TT_MMA_WAIT_FULL = 0, TT_MMA_WAIT_TEMPTY, TT_MMA_WAIT_HRFULL, TT_MMA_WAIT_D2EMPTY, TT_MMA_TOTAL, TT_EA_WAIT, TT_EA_BUSY,
-       TT_EB_WAIT, TT_EB_TMEM, TT_EB_EXCH, TT_EB_RESID, TT_EB_STORE, TT_EB_TOTAL, TT_KERNEL, TT_TILES, TT_SLOTS = 16 };
+       TT_EB_WAIT, TT_EB_TMEM, TT_EB_EXCH, TT_EB_RESID, TT_EB_STORE, TT_EB_TOTAL, TT_KERNEL, TT_TILES, TT_EB_TOP, TT_SLOTS = 16 };
 #define TT0() (TIMING ? clock64() : 0)
 #define TTACC(var, t0) do { if (TIMING) var += clock64() - (t0); } while (0)
 
@@ -339,8 +339,9 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
     auto run_b = [&](auto Rtag) {
     constexpr int R = decltype(Rtag)::value;
     int it = 0;
-    long long tb_wait = 0, tb_tmem = 0, tb_exch = 0, tb_resid = 0, tb_store = 0;
+    long long tb_wait = 0, tb_tmem = 0, tb_exch = 0, tb_resid = 0, tb_store = 0, tb_top = 0;
     const long long t_eb0 = TT0();
+    long long t_top0 = t_eb0;
     TileWalk tw(blockIdx.x, p.tiles_x, p.tiles_y, gridDim.x);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it, tw.next()) {
       const int img = tw.img, y0 = tw.y0(), x0 = tw.x0();
@@ -367,6 +368,7 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
           }
         }
       }
+      TTACC(tb_top, t_top0);
       long long t0 = TT0();
       mbar_wait(bar_d2full, (uint32_t)it & 1u, 8);
       TTACC(tb_wait, t0); t0 = TT0();
@@ -519,11 +521,12 @@ tail_tcgen05_kernel(const __grid_constant__ TailParams p) {
         }
       }
       TTACC(tb_store, t0);
+      t_top0 = TT0();
     }
     if (TIMING && warp == 12 && lane == 0) {
       unsigned long long* o = p.dbg + blockIdx.x * TT_SLOTS;
       o[TT_EB_WAIT] = tb_wait; o[TT_EB_TMEM] = tb_tmem; o[TT_EB_EXCH] = tb_exch; o[TT_EB_RESID] = tb_resid;
-      o[TT_EB_STORE] = tb_store; o[TT_EB_TOTAL] = clock64() - t_eb0;
+      o[TT_EB_STORE] = tb_store; o[TT_EB_TOTAL] = clock64() - t_eb0; o[TT_EB_TOP] = tb_top;
     }
     };
     if (warp < 16) run_b(std::integral_constant<int, 0>{}); else run_b(std::integral_constant<int, 1>{});

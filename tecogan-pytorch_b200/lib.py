@@ -28,7 +28,7 @@ class ConvDesc(ctypes.Structure):
         ('n', c_int32), ('h', c_int32), ('w', c_int32),
         ('cin', c_int32), ('cout', c_int32), ('cout_real', c_int32),
         ('kind', c_int32), ('act', c_int32), ('epilogue', c_int32),
-        ('a_mode', c_int32), ('max_ctas', c_int32), ('reserved', c_int32),
+        ('a_mode', c_int32), ('max_ctas', c_int32), ('cin_real', c_int32),
         ('mask', c_void_p),
     ]
 

@@ -134,6 +134,7 @@ class PackedConv:
         d.kind, d.act, d.epilogue = self.kind, self.act, (L.EPI_NHWC_F16_POOL2 if pool else self.epilogue)
         d.a_mode = default_a_mode() if a_mode is None else a_mode
         d.max_ctas = max_ctas
+        d.cin_real = self.cin_real
         impl = impl or default_conv_impl()
         lib = L.load()
         if impl == 'tcgen05':
@@ -502,6 +503,7 @@ class PackedDgrad:
         d.kind, d.epilogue = self.kind, L.EPI_NHWC_F16
         d.act = {L.ACT_NONE: L.ACT_NONE, L.ACT_RELU: L.ACT_DRELU, L.ACT_LRELU02: L.ACT_DLRELU02}[mask_act]
         d.a_mode = L.AMODE_AUTO
+        d.cin_real = self.fwd.cout_real          # dz channels beyond the layer's real outputs are zero
         impl = impl or default_conv_impl()
         lib = L.load()
         if impl == 'tcgen05':

@@ -167,7 +167,7 @@ def run_chain_ablate(n=4, h=134, w=320, blocks=10, max_ctas=0):
 
 TAIL_NAMES = ['mma_wait_full', 'mma_wait_tempty', 'mma_wait_hrfull', 'mma_wait_d2empty', 'mma_total', 'epiA_wait',
               'epiA_busy', 'epiB_wait', 'epiB_tmem', 'epiB_exchange', 'epiB_residual', 'epiB_store', 'epiB_total',
-              'kernel', 'tiles']
+              'kernel', 'tiles', 'epiB_top']
 
 
 def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True, accumulate=False):
@@ -201,7 +201,7 @@ def run_tail(flags='0', n=4, h=268, w=640, with_lr=True, with_u8=True, accumulat
     t = t[t[:, 13] > 0]
     tiles = t[:, 14].mean().item()
     out = {'flags': flags, 'lr': with_lr, 'u8': with_u8, 'accumulate': accumulate, 'us': round(us_plain, 1), 'tiles_per_cta': tiles,
-           'per_tile': {nm: round(t[:, i].mean().item() / max(tiles, 1)) for i, nm in enumerate(TAIL_NAMES[:14])}}
+           'per_tile': {nm: round(t[:, i].mean().item() / max(tiles, 1)) for i, nm in enumerate(TAIL_NAMES) if nm != 'tiles'}}
     print(json.dumps(out), flush=True)
     return out
 

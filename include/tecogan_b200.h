@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 2   /* 2: tg_conv_desc.mask, backward (training) entry points */
+#define TG_ABI_VERSION 2   /* 2: tg_conv_desc.mask, backward (training) entry points; tg_conv_desc.reserved became
+                              cin_real (0 keeps the old meaning: all stored input channels are used) */
 #define TG_TAPN_ROWS 48   /* 9 taps x 4 output channels, padded to a multiple of 16 */
 
 enum {

@@ -233,6 +233,42 @@ def check_conv_vs_simt(a_mode=None, cin=64, cout=64, h=134, w=320, n=1, kind=Non
     return {'rel_max': e, 'frac_diff': frac}
 
 
+def check_conv_issue_variants(kind=None, cin_real=64, cout_real=64, h=61, w=45, n=3, residual=False):
+    """The halo convs' issue variants are the same arithmetic in the same order and must agree BIT FOR BIT:
+    two MMA issuer warps (default) vs one (TG_DBG_FLAGS=16, read per launch), and the thin-layer k-step skip
+    (tg_conv_desc.cin_real) vs all four k-steps (cin_real = 0: the skipped products are x * 0)."""
+    kind = L.CONV_3X3 if kind is None else kind
+    cin, cout = 64, 64
+    x = nhwc(rand(140, n, cin_real, h, w, lo=-1, hi=1), cin)
+    bound = 1.5 / np.sqrt(9 * cin_real)
+    wshape = (cout_real, cin_real, 3, 3) if kind == L.CONV_3X3 else (cin_real, cout_real, 3, 3)
+    pc = ops.PackedConv(rand(141, *wshape, lo=-bound, hi=bound).to(DEV),
+                        rand(142, cout_real, lo=-0.5, hi=0.5).to(DEV), kind, L.ACT_RELU)
+    res = nhwc(rand(143, n, cout_real, h, w, lo=-1, hi=1), cout) if (residual and kind == L.CONV_3X3) else None
+    old = os.environ.get('TG_DBG_FLAGS')
+    try:
+        os.environ.pop('TG_DBG_FLAGS', None)
+        dual = pc(x, residual=res, impl='tcgen05', a_mode=L.AMODE_HALO)
+        real = pc.cin_real
+        pc.cin_real = 0                                  # descriptor says: every stored input channel may be non-zero
+        dual_all_k = pc(x, residual=res, impl='tcgen05', a_mode=L.AMODE_HALO)
+        pc.cin_real = real
+        os.environ['TG_DBG_FLAGS'] = '16'
+        single = pc(x, residual=res, impl='tcgen05', a_mode=L.AMODE_HALO)
+    finally:
+        if old is None:
+            os.environ.pop('TG_DBG_FLAGS', None)
+        else:
+            os.environ['TG_DBG_FLAGS'] = old
+    ref = pc(x, residual=res, impl='simt')
+    torch.cuda.synchronize()
+    assert torch.equal(dual, single), 'two issuers vs one issuer differ'
+    assert torch.equal(dual, dual_all_k), 'k-step skip (cin_real) changed the result'
+    e = float((dual.float() - ref.float()).abs().max() / ref.float().abs().max())
+    assert e <= 2e-3, f'tcgen05 vs simt: rel max {e}'
+    return {'bit_identical': True, 'rel_max_vs_simt': e}
+
+
 def check_conv_chain(n=2, h=37, w=29, blocks=2, max_ctas=0, repeats=1, seed=50):
     """tg_conv_chain_tcgen05 (conv_in + `blocks` residual blocks in ONE persistent launch, tiles
     gated by progress flags) vs the same layers as 1+2*blocks launches of tg_conv_tcgen05 on
@@ -1224,6 +1260,10 @@ CHECKS = {
     'conv_tc_vs_simt_halo_full': lambda: check_conv_vs_simt(L.AMODE_HALO),
     'conv_tc_vs_simt_halo_convT_full': lambda: check_conv_vs_simt(L.AMODE_HALO, kind=L.CONVT_3X3_S2),
     'conv_tc_vs_simt_halo_2cta': lambda: check_conv_vs_simt(L.AMODE_HALO, h=64, w=64, n=2, max_ctas=3),
+    'conv_issue_variants_64': lambda: check_conv_issue_variants(residual=True),
+    'conv_issue_variants_thin_6_32': lambda: check_conv_issue_variants(cin_real=6, cout_real=32),
+    'conv_issue_variants_thin_32_64': lambda: check_conv_issue_variants(cin_real=32, cout_real=64, h=33, w=80),
+    'conv_issue_variants_convT': lambda: check_conv_issue_variants(kind=L.CONVT_3X3_S2, h=24, w=40, n=2),
     'conv_chain_vs_reference': check_conv_chain_vs_reference,
     'conv_chain_1tile': lambda: check_conv_chain(n=1, h=16, w=8, blocks=1),
     'conv_chain_ragged_repeat': lambda: check_conv_chain(n=2, h=37, w=29, blocks=2, repeats=3),

@@ -98,6 +98,9 @@ def test_null_and_bad_arguments_are_rejected_without_a_gpu():
     d.x = d.weights = d.bias = d.y = 16
     d.n, d.h, d.w, d.cin, d.cout = 1, 8, 8, 48, 64
     assert lib.tg_conv_tcgen05(ctypes.byref(d), None) == -2      # cin must be 64/128/256
+    d.cin, d.cin_real = 64, 65                                   # real input channels beyond the stored ones
+    assert lib.tg_conv_tcgen05(ctypes.byref(d), None) == -1 and b'cin_real' in lib.tg_last_error_string()
+    assert L.ConvDesc.cin_real.offset == 40 + 11 * 4             # the former `reserved` slot: layout unchanged
     with pytest.raises(L.TecoganB200Error):
         L.check(-2, 'tg_conv_tcgen05')
 

@@ -2,7 +2,7 @@
 // warp-specialised tcgen05 launch for sm_100a -- the layer loop lives inside the kernel.
 //
 //   tiles   : 16x8 output pixels (M = 128), static assignment tile = cta + k*grid for every layer
-//   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 4 stages; the nine
+//   A       : one 18x10 halo box per tile by TMA (zero fill = conv padding), 3 stages; the nine
 //             taps are nine shifted UMMA-descriptor views of the box (see tg_conv_tcgen05.cu)
 //   B       : packed weights double-buffered in smem (layer l in buffer l & 1, 72 KB each): layer l+1
 //             streams in (one bulk copy) as soon as both MMA issuers have retired layer l-1 -- a whole
@@ -11,8 +11,9 @@
 //             over two partial accumulators was measured: no gain).
 //   layers  : a tile of layer l needs the tiles of layer l-1 under its halo.  Epilogue groups
 //             publish `flags[tile] = epoch*32 + l + 1` (release, gpu scope) after their stores; a
-//             checker warp polls the <= 9 flags of each of the next nine tiles (sliding window)
-//             ahead of the TMA producer and hands it an in-order "verified" counter.  No launch,
+//             checker warp polls the <= 9 flags of each of the next three tiles (sliding window, one
+//             load per lane and round) ahead of the TMA producer and hands it an in-order "verified"
+//             counter.  No launch,
 //             pipeline fill/drain, weight reload bubble or grid barrier between layers.
 //   roles   : warp 0 TMA producer, warps 1 and 12 MMA issuers (even / odd tiles of the CTA's sequence),
 //             warp 2 TMEM allocator + weight streamer, warp 3 dependency checker, warps 4..11 two

@@ -19,10 +19,11 @@
 namespace {
 
 constexpr int kWarpsPerCta = 4;
+constexpr int kDefaultOcc = 5;
 
 // FLOW: 0 = HR flow given; 1 / 2 = LR flow upsampled inline with the bicubic / bilinear upsample_func
-template <int S, int FLOW>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, 5)
+template <int S, int FLOW, int OCC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, OCC)
 warp_s2d_concat_w_kernel(const float* __restrict__ hr_prev, const float* __restrict__ flow,
                          const float* __restrict__ lr_curr, __half* __restrict__ out, int n, int h, int w,
                          int h8, int w8, int cpad) {
@@ -219,15 +220,24 @@ cudaError_t tg_warp_w_launch(const float* hr_prev, const float* flow, const floa
   const size_t smem = per_warp * kWarpsPerCta;
   const long long units = (long long)n * h * ((w + lrw - 1) / lrw);
   long long ctas = (units + kWarpsPerCta - 1) / kWarpsPerCta;
-  const long long cap = 148 * 5;                 // one resident wave (5 CTAs per SM): every warp walks ~7 units and
-                                                 // the warps of an SM drift out of phase
+  // resident CTAs per SM (register cap 65536 / (128 * OCC)): TG_WARP_OCC = 5..8 for A/B measurements
+  static int occ = 0;
+  if (occ == 0) {
+    const char* e = getenv("TG_WARP_OCC");
+    occ = e != nullptr ? atoi(e) : kDefaultOcc;
+    if (occ < 5 || occ > 8) occ = kDefaultOcc;
+  }
+  const long long cap = 148LL * occ;             // one resident wave: every warp walks several units and the warps
+                                                 // of an SM drift out of phase
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
   dim3 grid((unsigned)ctas), block(32 * kWarpsPerCta);
-#define TG_W(SS, FM) return tg_launch(warp_s2d_concat_w_kernel<SS, FM>, grid, block, smem, st, hr_prev, flow, lr_curr, out, n, h, w, h8, w8, cpad)
+#define TG_W3(SS, FM, OC) return tg_launch(warp_s2d_concat_w_kernel<SS, FM, OC>, grid, block, smem, st, hr_prev, flow, lr_curr, out, n, h, w, h8, w8, cpad)
+#define TG_W(SS, FM) do { if (occ == 5) TG_W3(SS, FM, 5); if (occ == 6) TG_W3(SS, FM, 6); if (occ == 7) TG_W3(SS, FM, 7); TG_W3(SS, FM, 8); } while (0)
   if (s == 4) { if (fm == 0) TG_W(4, 0); if (fm == 1) TG_W(4, 1); TG_W(4, 2); }
   if (fm == 0) TG_W(2, 0);
   if (fm == 1) TG_W(2, 1);
   TG_W(2, 2);
 #undef TG_W
+#undef TG_W3
 }

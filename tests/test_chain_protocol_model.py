@@ -322,6 +322,8 @@ SHAPES = [
     (5, 2, 1, 1, 3),      # a single CTA owning everything
     (2, 2, 1, 3, 1),      # a chain of one layer
     (6, 2, 1, 2, 2),      # first tile of layer 1 is also the last-but-n of layer 0
+    (8, 4, 2, 13, 6),     # 4-5 tiles per CTA, two images, odd / even tile counts mixed
+    (5, 3, 1, 2, 7),      # 7-8 tiles per CTA: the issuers' last tiles of a layer fall on different parities
 ]
 
 

@@ -5,7 +5,7 @@
 // answers, per variant: how long the issuing thread is held per MMA, how long the tensor pipe needs
 // per MMA, and how much unrelated work between MMAs the pipe's queue hides.
 //
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/_build/mma_probe tools/mma_probe.cu
+//   make -C tecogan-pytorch_b200/csrc probe      (nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17)
 //   tools/_build/mma_probe            (prints one line per variant, cycles of CTA 0 / median over CTAs)
 #include <cstdio>
 #include <cstdlib>
